@@ -1,0 +1,173 @@
+/*
+ * b200aug.h -- C ABI of the B200-native augmentation / label-transform hot path.
+ *
+ * The reference (opentrack/neuralnet-tracker-traincode) has no native or FFI interface for this path: the
+ * boundary is the Python protocol `Callable[[Batch], Batch]`.  Each entry point below names the
+ * reference function(s) (file:line, relative to the reference checkout) whose arithmetic it replaces; the Python
+ * mirror of the reference API (neuralnet-tracker-traincode_b200/trackertraincode_b200) binds them with ctypes,
+ * see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors); nothing is allocated or freed here;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and is
+ *     asynchronous; calls on distinct streams are thread-safe;
+ *   - return value: 0 on success, a B200AUG_E_* code otherwise (b200aug_strerror() explains it);
+ *   - per-sample problems (empty crop box, unsupported resampler) do not fail the launch: they are reported in the
+ *     optional device array `status_out[B]` and the sample's image is zero-filled;
+ *   - images are single-channel (the pose pipeline loads monochrome, dshdf5pose.py:201); layouts:
+ *       source  uint8  [H, W]      row pitch in bytes, one descriptor per sample (ragged batches allowed)
+ *       crop    uint8  [B, 1, oh, ow]   or   float32 [B, 1, oh, ow]
+ *       roi [x0,y0,x1,y1] - coord [x,y,size] - quaternion [i,j,k,w] - points [n, 2|3]   (all float32)
+ */
+#ifndef B200AUG_H_
+#define B200AUG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AUG_ABI_VERSION 1
+
+/* error codes */
+#define B200AUG_OK 0
+#define B200AUG_E_INVALID_ARG 1   /* NULL where a pointer is required, non-positive sizes, bad flag combination */
+#define B200AUG_E_UNSUPPORTED 2   /* valid request the kernels do not cover (e.g. rot90 on non-square output) */
+#define B200AUG_E_SMEM 3          /* requested row-buffer capacity does not fit in 227 KB of shared memory */
+#define B200AUG_E_CUDA 4          /* the CUDA runtime reported an error at launch; see b200aug_last_cuda_error() */
+
+/* per-sample status codes written to status_out */
+#define B200AUG_S_OK 0
+#define B200AUG_S_EMPTY_BOX 1     /* view box with non-positive width/height (cv2.resize would throw) */
+#define B200AUG_S_UNSUPPORTED 2   /* INTER_AREA with one axis up-scaling (unreachable from GeneralFocusRoi) */
+#define B200AUG_S_ROWBUF 3        /* source segment needed by 160 output columns exceeds rowbuf_capacity */
+
+/* field categories: FieldCategory, trackertraincode/datasets/dshdf5pose.py:21-28 */
+#define B200AUG_CAT_GENERAL 0     /* ""    passes through unchanged */
+#define B200AUG_CAT_QUAT 1        /* "q"   affinetrafo.py:98-127  transform_rot */
+#define B200AUG_CAT_XYS 2         /* "xys" affinetrafo.py:89-95   transform_coord */
+#define B200AUG_CAT_ROI 3         /* "roi" affinetrafo.py:75-86   transform_roi */
+#define B200AUG_CAT_POINTS 4      /* "pts" affinetrafo.py:37-72   transform_keypoints (68-landmark flip_map) */
+
+/* stage flags of b200aug_fused_forward, in pipeline order (trackertraincode/pipelines.py:372-383, 508-532) */
+#define B200AUG_F_HALF_PIXEL 0x01u         /* offset_points_by_half_pixel       batch/normalization.py:83-90 */
+#define B200AUG_F_ROI_FROM_LANDMARKS 0x02u /* PutRoiFromLandmarks before+after  batch/misc.py:9-31 (no forehead ext.) */
+#define B200AUG_F_FOCUS 0x04u              /* GeneralFocusRoi.__call__          batch/geometric.py:193-231 */
+#define B200AUG_F_FLIPROT 0x08u            /* horizontal_flip_and_rot_90        batch/geometric.py:234-267 */
+#define B200AUG_F_NORMALIZE 0x10u          /* normalize_batch                   batch/normalization.py:20-56 */
+#define B200AUG_F_PHOTOMETRIC 0x20u        /* KorniaImageDistortions x2         batch/intensity.py:30-64, pipelines.py:508-527 */
+#define B200AUG_F_WHITEN 0x40u             /* whiten_batch                      batch/normalization.py:94-99 */
+
+#define B200AUG_MAX_FIELDS 8
+#define B200AUG_NUM_OPS 6
+#define B200AUG_NUM_NOISE 4
+
+/* stage-1 photometric op ids (order of the AugmentationSequential children, pipelines.py:511-518) */
+#define B200AUG_OP_EQUALIZE 0
+#define B200AUG_OP_POSTERIZE 1
+#define B200AUG_OP_GAMMA 2
+#define B200AUG_OP_CONTRAST 3
+#define B200AUG_OP_BRIGHTNESS 4
+#define B200AUG_OP_BLUR 5
+
+/* One source image (device memory). */
+typedef struct B200AugSrc {
+  const uint8_t* ptr; /* top-left pixel */
+  int32_t width;
+  int32_t height;
+  int32_t pitch;      /* bytes between rows */
+  int32_t reserved;
+} B200AugSrc;
+
+/* One label tensor [B, count, dim] float32, transformed according to `category`. in == out is allowed for every
+ * category except POINTS with count == 68 (the mirror permutation reads other rows). */
+typedef struct B200AugField {
+  int32_t category;
+  int32_t count;      /* items per sample (68 landmarks, 1 roi, ...) */
+  int32_t dim;        /* floats per item: roi 4, xys 3, quat 4, points 2 or 3, general any */
+  int32_t reserved;
+  const float* in;
+  float* out;
+} B200AugField;
+
+/* Sampled parameters of the two photometric stages for one call (pipelines.py:510-527).  `order` lists the
+ * stage-1 children chosen by random_apply (one draw per call), in application order. */
+typedef struct B200AugPhotoParams {
+  int32_t n_order;
+  int32_t order[B200AUG_NUM_OPS];
+  int32_t clip;                 /* OnlyClip(p=1): clamp to [0,1] after the noise stages */
+  const uint8_t* apply;         /* [B, 6] per-sample Bernoulli masks, indexed by op id */
+  const int32_t* bits;          /* [B] posterize bits */
+  const float* gamma;           /* [B] */
+  const float* contrast;        /* [B] */
+  const float* brightness;      /* [B] */
+  const uint8_t* noise_apply;   /* [B, 4] */
+  float noise_std[B200AUG_NUM_NOISE];
+  uint64_t seed;                /* Philox4x32-10 key */
+  uint64_t sample_offset;       /* id of sample 0 in the noise stream (rank * local batch + step * global batch ...) */
+} B200AugPhotoParams;
+
+typedef struct B200AugFusedArgs {
+  int32_t struct_size;          /* sizeof(B200AugFusedArgs), checked */
+  int32_t batch;
+  int32_t out_w, out_h;         /* crop size (129 x 129 for the pose net) */
+  uint32_t flags;               /* B200AUG_F_* */
+  int32_t rowbuf_capacity;      /* bytes of staged source row per warp slot; 0 = default (1024) */
+
+  /* sources: a table of descriptors (ragged batch) or, if NULL, one descriptor + stride (stacked [B,H,W] tensor) */
+  const B200AugSrc* src_table;
+  B200AugSrc src_uniform;
+  int64_t src_stride;           /* bytes between consecutive images when src_table == NULL */
+
+  /* RoiFocusRandomizationParameters (batch/geometric.py:27-32), device arrays */
+  const float* scales;          /* [B] */
+  const float* angles;          /* [B] radians; pixel path is croprescale iff angle == 0 (geometric.py:210) */
+  const float* cos_sin;         /* optional [B,2]: host-evaluated torch.cos/sin(angles) (affine2d.py:46-47) */
+  const float* translations;    /* [B,2] */
+  float beyond_border_shift;    /* 0.3, geometric.py:104 */
+  /* horizontal_flip_and_rot_90 draws (batch/geometric.py:236-237) */
+  const uint8_t* do_flip;       /* [B] or NULL */
+  const int8_t* rot_dir;        /* [B] in {-1,0,1} or NULL */
+
+  /* labels */
+  int32_t n_fields;
+  int32_t roi_field;            /* index into fields of the focus box (roi_variable), -1 if F_ROI_FROM_LANDMARKS only */
+  int32_t landmark_field;       /* index of pt3d_68 for F_ROI_FROM_LANDMARKS, else -1 */
+  int32_t reserved;
+  B200AugField fields[B200AUG_MAX_FIELDS];
+
+  /* outputs (each may be NULL) */
+  int32_t* view_roi_out;        /* [B,4] rounded view box, geometric.py:205 */
+  float* tr_out;                /* [B,2,3] focus transform, geometric.py:206-207 */
+  float* backtransform_out;     /* [B,2,3] tr^-1, geometric.py:226-227 */
+  uint8_t* image_u8_out;        /* [B,1,oh,ow] when F_NORMALIZE is not set */
+  float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
+  int32_t* status_out;          /* [B] B200AUG_S_* */
+
+  B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
+} B200AugFusedArgs;
+
+int b200aug_abi_version(void);
+const char* b200aug_strerror(int code);
+/* cudaError_t (as int) of the last failed launch on this host thread, 0 if none */
+int b200aug_last_cuda_error(void);
+/* dynamic shared memory (bytes) one CTA of the fused kernel uses for this geometry; 0 if it cannot fit */
+size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capacity);
+
+/* The fused hot path: one launch, one CTA per sample.
+ * Replaces, per the flags: batch/normalization.py:83-90, batch/misc.py:9-31, batch/geometric.py:107-231
+ * (+ tensors/image_geometric_cv2.py:28-155 incl. cv2.warpAffine / cv2.resize arithmetic, tensors/affinetrafo.py:37-148),
+ * batch/geometric.py:234-267, batch/normalization.py:20-56, batch/intensity.py:30-64, batch/normalization.py:94-99. */
+int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream);
+
+/* apply_affine2d (tensors/affinetrafo.py:130-148) on label tensors with an explicit transform per sample
+ * (tr [B,2,3], or one [2,3] broadcast when tr_stride == 0). */
+int b200aug_apply_affine2d(const float* tr, int64_t tr_stride, int batch, int n_fields, const B200AugField* fields,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AUG_H_ */

@@ -1,0 +1,330 @@
+"""Marshals a `Batch` into one call of the fused CUDA kernel (include/b200aug.h: b200aug_fused_forward).
+
+Everything here is host-side plumbing: pointer/shape bookkeeping, output allocation, parameter upload.  The
+arithmetic of the path lives in csrc/.  No CPU fallback exists: tensors must be on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..datasets.batch import Batch, FieldCategory, as_category, imagelike_categories
+
+_CAT_CODE = {
+    FieldCategory.quat: N.CAT_QUAT,
+    FieldCategory.xys: N.CAT_XYS,
+    FieldCategory.roi: N.CAT_ROI,
+    FieldCategory.points: N.CAT_POINTS,
+}
+_CAT_DIMS = {N.CAT_QUAT: (4,), N.CAT_XYS: (3,), N.CAT_ROI: (4,), N.CAT_POINTS: (2, 3)}
+
+STATUS_TEXT = {N.S_EMPTY_BOX: "empty view box", N.S_UNSUPPORTED: "unsupported resampler (INTER_AREA with one axis up-scaling)",
+               N.S_ROWBUF: "source segment exceeds rowbuf_capacity"}
+
+
+@dataclass
+class GeoParams:
+    """RoiFocusRandomizationParameters (+ optional host-evaluated cos/sin) as device tensors."""
+
+    scales: torch.Tensor
+    angles: torch.Tensor
+    translations: torch.Tensor
+    cos_sin: Optional[torch.Tensor] = None
+
+
+@dataclass
+class PhotoParams:
+    """One call's draws of the two KorniaImageDistortions stages (see include/b200aug.h: B200AugPhotoParams)."""
+
+    order: Sequence[int]
+    apply: torch.Tensor  # bool/uint8 [B, 6]
+    bits: torch.Tensor  # int32 [B]
+    gamma: torch.Tensor  # float32 [B]
+    contrast: torch.Tensor
+    brightness: torch.Tensor
+    noise_apply: torch.Tensor  # bool/uint8 [B, 4]
+    noise_std: Sequence[float] = (4.0 / 255.0, 16.0 / 255.0, 32.0 / 255.0, 64.0 / 255.0)
+    seed: int = 0
+    sample_offset: int = 0
+    clip: bool = True
+
+
+@dataclass
+class FusedResult:
+    batch: Batch
+    view_roi: Optional[torch.Tensor] = None
+    tr: Optional[torch.Tensor] = None
+    status: Optional[torch.Tensor] = None
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise N.NativeError(f"{what} must live on a CUDA device (got {t.device}); this path has no CPU implementation")
+
+
+def _dev(t, device, dtype) -> torch.Tensor:
+    t = torch.as_tensor(t)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def host_cos_sin(angles: torch.Tensor) -> Optional[torch.Tensor]:
+    """cos/sin evaluated exactly like the reference does on the host (Affine2d.trs, affine2d.py:46-47); None when the
+    angles already live on the device (the kernel then uses the correctly rounded values)."""
+    if angles.is_cuda:
+        return None
+    a = angles.to(torch.float32)
+    return torch.stack([torch.cos(a), torch.sin(a)], dim=-1)
+
+
+class _ImageSource:
+    """Single-channel uint8 sources of one image field: stacked tensor or ragged list -> kernel descriptors."""
+
+    def __init__(self, value, batched: bool, device):
+        self.keep: List[Any] = []
+        self.table = None
+        self.uniform = N.Src()
+        self.stride = 0
+        if isinstance(value, (list, tuple)):
+            imgs = [self._hw(v) for v in value]
+            tab = np.zeros((len(imgs), 6), dtype=np.int32)
+            ptrs = tab[:, :2].view(np.int64)
+            for i, im in enumerate(imgs):
+                _require_cuda(im, "image")
+                ptrs[i, 0] = im.data_ptr()
+                tab[i, 2], tab[i, 3], tab[i, 4] = im.shape[1], im.shape[0], im.stride(0)
+            self.keep += imgs
+            self.table = torch.from_numpy(tab).to(device, non_blocking=True)
+            self.n = len(imgs)
+            self.wh = None
+            return
+        v = value if batched else value[None]
+        _require_cuda(v, "image")
+        if v.dtype != torch.uint8:
+            raise TypeError(f"image must be uint8, got {v.dtype}")
+        if v.dim() == 4:
+            if v.shape[-1] == 1:
+                v = v[..., 0]
+            elif v.shape[1] == 1:
+                v = v[:, 0]
+            else:
+                raise N.NativeError("only single-channel images are supported on this path")
+        assert v.dim() == 3, f"bad image shape {tuple(value.shape)}"
+        if v.stride(2) != 1:
+            v = v.contiguous()
+        self.keep.append(v)
+        self.uniform = N.Src(v.data_ptr(), v.shape[2], v.shape[1], v.stride(1), 0)
+        self.stride = v.stride(0)
+        self.n = v.shape[0]
+        self.wh = (v.shape[2], v.shape[1])
+
+    @staticmethod
+    def _hw(t: torch.Tensor) -> torch.Tensor:
+        if t.dtype != torch.uint8:
+            raise TypeError(f"image must be uint8, got {t.dtype}")
+        if t.dim() == 3:
+            if t.shape[-1] == 1:
+                t = t[..., 0]
+            elif t.shape[0] == 1:
+                t = t[0]
+            else:
+                raise N.NativeError("only single-channel images are supported on this path")
+        if t.stride(1) != 1:
+            t = t.contiguous()
+        return t
+
+
+def fused_forward(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams] = None,
+                  do_flip: Optional[torch.Tensor] = None, rot_dir: Optional[torch.Tensor] = None,
+                  photo: Optional[PhotoParams] = None, roi_variable: str = "roi", landmark_variable: str = "pt3d_68",
+                  beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
+                  want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None) -> FusedResult:
+    """Run the stages selected by `flags` on every field of `batch` in one kernel launch; returns a new Batch."""
+    meta = batch.meta
+    batched = meta.prefixshape != ()
+    (B,) = meta.prefixshape if batched else (1,)
+    ow, oh = (out_size, out_size) if isinstance(out_size, int) else tuple(out_size)
+    device = batch.device
+    if device.type != "cuda":
+        raise N.NativeError(f"batch lives on {device}; the B200 path needs CUDA tensors (there is no CPU fallback)")
+
+    args = N.FusedArgs()
+    args.struct_size = C.sizeof(N.FusedArgs)
+    args.batch, args.out_w, args.out_h, args.flags = B, ow, oh, flags
+    args.rowbuf_capacity = rowbuf_capacity
+    args.beyond_border_shift = beyond_border_shift
+    args.roi_field = args.landmark_field = -1
+    keep: List[Any] = []
+    out_data: Dict[str, Any] = {}
+
+    # ---- fields
+    image_keys = [k for k in batch.keys() if as_category(meta.categories.get(k)) == FieldCategory.image]
+    if image_key is not None:
+        image_keys = [image_key]
+    if len(image_keys) > 1:
+        raise N.NativeError("one image field per call")  # TODO(next): loop over image-like fields
+    nf = 0
+    pending: List[Tuple[str, torch.Tensor, tuple]] = []
+    for k, v in batch.items():
+        cat = as_category(meta.categories.get(k))
+        if cat in imagelike_categories:
+            if cat == FieldCategory.semseg:
+                raise N.NativeError("semseg fields are not on the B200 path")
+            continue
+        code = _CAT_CODE.get(cat)
+        if code is None or not isinstance(v, torch.Tensor) or not v.is_floating_point() or k == "image_backtransform":
+            out_data[k] = v
+            continue
+        _require_cuda(v, k)
+        t = v if batched else v[None]
+        t = t.to(torch.float32).contiguous()
+        if t.shape[-1] not in _CAT_DIMS[code]:
+            raise ValueError(f"field {k!r} of category {cat.value!r} has last dim {t.shape[-1]}")
+        dim = t.shape[-1]
+        count = int(np.prod(t.shape[1:-1])) if t.dim() > 2 else 1
+        if nf >= N.MAX_FIELDS:
+            raise N.NativeError(f"more than {N.MAX_FIELDS} label fields")
+        o = torch.empty_like(t)
+        f = args.fields[nf]
+        f.category, f.count, f.dim, f.inp, f.out = code, count, dim, t.data_ptr(), o.data_ptr()
+        if k == roi_variable:
+            args.roi_field = nf
+        if k == landmark_variable:
+            args.landmark_field = nf
+        keep += [t, o]
+        pending.append((k, o, tuple(v.shape)))
+        nf += 1
+    args.n_fields = nf
+
+    # ---- parameters
+    f32, u8 = torch.float32, torch.uint8
+    if flags & N.F_FOCUS:
+        assert geo is not None
+        sc = _dev(geo.scales, device, f32).reshape(B)
+        an = _dev(geo.angles, device, f32).reshape(B)
+        tr_ = _dev(geo.translations, device, f32).reshape(B, 2)
+        keep += [sc, an, tr_]
+        args.scales, args.angles, args.translations = sc.data_ptr(), an.data_ptr(), tr_.data_ptr()
+        if geo.cos_sin is not None:
+            cs = _dev(geo.cos_sin, device, f32).reshape(B, 2)
+            keep.append(cs)
+            args.cos_sin = cs.data_ptr()
+    if flags & N.F_FLIPROT:
+        if do_flip is not None:
+            df = _dev(do_flip, device, u8).reshape(B)
+            keep.append(df)
+            args.do_flip = df.data_ptr()
+        if rot_dir is not None:
+            rd = _dev(rot_dir, device, torch.int8).reshape(B)
+            keep.append(rd)
+            args.rot_dir = rd.data_ptr()
+    if flags & N.F_PHOTOMETRIC:
+        assert photo is not None
+        p = args.photo
+        p.n_order = len(photo.order)
+        for i, op in enumerate(photo.order):
+            p.order[i] = int(op)
+        p.clip = int(photo.clip)
+        ap = _dev(photo.apply, device, u8).reshape(B, N.NUM_OPS)
+        bi = _dev(photo.bits, device, torch.int32).reshape(B)
+        ga = _dev(photo.gamma, device, f32).reshape(B)
+        co = _dev(photo.contrast, device, f32).reshape(B)
+        br = _dev(photo.brightness, device, f32).reshape(B)
+        na = _dev(photo.noise_apply, device, u8).reshape(B, N.NUM_NOISE)
+        keep += [ap, bi, ga, co, br, na]
+        p.apply, p.bits, p.gamma, p.contrast, p.brightness, p.noise_apply = (t.data_ptr() for t in (ap, bi, ga, co, br, na))
+        for i, s in enumerate(photo.noise_std):
+            p.noise_std[i] = float(s)
+        p.seed, p.sample_offset = int(photo.seed) & (2**64 - 1), int(photo.sample_offset)
+
+    # ---- image
+    img_out = None
+    if image_keys:
+        src = _ImageSource(batch[image_keys[0]], batched, device)
+        assert src.n == B, f"image count {src.n} != batch {B}"
+        keep.append(src)
+        if src.table is not None:
+            args.src_table = src.table.data_ptr()
+        else:
+            args.src_uniform, args.src_stride = src.uniform, src.stride
+        if not (flags & N.F_FOCUS) and src.wh is not None and src.wh != (ow, oh):
+            raise ValueError(f"without the focus stage images must already be {ow}x{oh}, got {src.wh}")
+        if flags & N.F_NORMALIZE:
+            img_out = torch.empty((B, 1, oh, ow), dtype=f32, device=device)
+            args.image_f32_out = img_out.data_ptr()
+        else:
+            img_out = torch.empty((B, 1, oh, ow), dtype=u8, device=device)
+            args.image_u8_out = img_out.data_ptr()
+
+    view_roi = tr = status = None
+    if flags & N.F_FOCUS:
+        if want_view_roi:
+            view_roi = torch.empty((B, 4), dtype=torch.int32, device=device)
+            args.view_roi_out = view_roi.data_ptr()
+        tr = torch.empty((B, 2, 3), dtype=f32, device=device)
+        args.tr_out = tr.data_ptr()
+        if insert_backtransform:
+            bt = torch.empty((B, 2, 3), dtype=f32, device=device)
+            args.backtransform_out = bt.data_ptr()
+    if want_status:
+        status = torch.empty((B,), dtype=torch.int32, device=device)
+        args.status_out = status.data_ptr()
+
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        N.check(N.lib.b200aug_fused_forward(C.byref(args), C.c_void_p(stream)), "b200aug_fused_forward")
+
+    # ---- assemble the result
+    new_meta = meta
+    for k, o, shape in pending:
+        out_data[k] = o.reshape(shape)
+    if image_keys:
+        out_data[image_keys[0]] = img_out if batched else img_out[0]
+    if (flags & N.F_FOCUS) and insert_backtransform:
+        out_data["image_backtransform"] = bt if batched else bt[0]
+    # keep the reference's key order
+    ordered = {k: out_data[k] for k in batch.keys() if k in out_data}
+    ordered.update((k, v) for k, v in out_data.items() if k not in ordered)
+    res = FusedResult(Batch(new_meta, ordered), view_roi, tr, status)
+    res._keep = keep  # inputs must outlive the asynchronous launch
+    return res
+
+
+def raise_on_status(status: torch.Tensor):
+    """Synchronising check of the per-sample status array (debug / tests)."""
+    s = status.cpu().numpy()
+    bad = np.nonzero(s)[0]
+    if bad.size:
+        raise N.NativeError("; ".join(f"sample {i}: {STATUS_TEXT.get(int(s[i]), s[i])}" for i in bad[:8]))
+
+
+def apply_affine2d_fields(tr: torch.Tensor, fields: List[Tuple[FieldCategory, torch.Tensor]]) -> List[torch.Tensor]:
+    """b200aug_apply_affine2d on [B, ...] label tensors; `tr` is [B,2,3] or [2,3] (broadcast)."""
+    dev = tr.device
+    _require_cuda(tr, "transform")
+    tr = tr.to(torch.float32).contiguous()
+    B = fields[0][1].shape[0]
+    arr = (N.Field * len(fields))()
+    outs, keep = [], []
+    for i, (cat, t) in enumerate(fields):
+        code = _CAT_CODE.get(as_category(cat), N.CAT_GENERAL)
+        t = t.to(torch.float32).contiguous()
+        o = torch.empty_like(t)
+        arr[i].category, arr[i].dim = code, t.shape[-1]
+        arr[i].count = int(np.prod(t.shape[1:-1])) if t.dim() > 2 else 1
+        arr[i].inp, arr[i].out = t.data_ptr(), o.data_ptr()
+        outs.append(o)
+        keep.append(t)
+    stride = 6 if tr.dim() == 3 else 0
+    with torch.cuda.device(dev):
+        N.check(N.lib.b200aug_apply_affine2d(C.c_void_p(tr.data_ptr()), stride, B, len(fields), arr,
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "b200aug_apply_affine2d")
+    return outs

@@ -1,0 +1,5 @@
+from ...datasets.batch import FieldCategory, imagelike_categories  # noqa: F401
+from .geometric import (  # noqa: F401
+    FocusRoi, GeneralFocusRoi, MakeRoiRandomizationParameters, NoRoiRandomization, RandomFocusRoi,
+    RoiFocusRandomizationParameters, horizontal_flip_and_rot_90)
+from .normalization import normalize_batch, offset_points_by_half_pixel, unnormalize_batch, whiten_batch  # noqa: F401
