@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the augmentation / label-transform hot path (BASELINE.json metric: augmented samples/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  CPU implementation on the host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "config 2"): synthetic 300W-LP-shaped batch -- 450x450 uint8 gray
+sources -> 129x129 float32 crops, batch 512 per GPU, full geometric (crop/scale/translate, 1/3 rotated by +-30 deg, flip,
+rot90) + photometric (equalize/posterize/gamma/contrast/brightness/blur, 4 noise stages, clip) + whiten + all labels.
+One step = one pass of the hot path over one batch.  Prints ONE JSON line (rank 0).
+
+value      whole-job samples/s with sources and sampled parameters resident in HBM (the fused kernel alone)
+e2e        samples/s through the public API (`FusedPoseAugmentation(batch)`) from pinned HOST buffers: per step the
+           H2D copy of the uint8 frames + labels, host-side parameter sampling + upload, the kernel, and a D2H read of
+           the transformed labels
+roofline   algorithmic bytes (clipped view-box pixels x 1 B + output x 4 B + label bytes) / event-timed kernel duration
+           against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline  the oracle port (numpy + cv2, one process per host core) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "neuralnet-tracker-traincode_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+BATCH = 512
+SRC = 450
+OUT = 129
+RING = 4  # distinct batches resident in HBM: 4 x 104 MB of sources > 126 MB L2
+WORKLOAD = ("config2: synthetic 300W-LP-shaped, 450x450 u8 gray -> 129x129 f32, batch 512 per GPU, "
+            "full geometric+photometric+labels")
+LABEL_BYTES = 2 * (68 * 3 * 4 + 16 + 16 + 12) + 40
+
+
+# ----------------------------------------------------------------------------------------------- synthetic workload
+
+def make_host_batch(seed: int, n: int = BATCH):
+    """Sources + labels of SURVEY.md 8d config 2, numpy on the host."""
+    rng = np.random.default_rng(seed)
+    img = np.empty((n, SRC, SRC), np.uint8)
+    half = n // 2
+    img[:half] = rng.integers(0, 256, (half, SRC, SRC), dtype=np.uint8)  # (i) uniform noise
+    y, x = np.mgrid[0:SRC, 0:SRC].astype(np.float32)
+    base = (np.sin(x / 17.0) + np.cos(y / 23.0) + 2.0) / 4.0 * 255.0  # (ii) smooth field + N(0, 8)
+    for i in range(half, n):
+        img[i] = np.clip(np.rint(base + rng.standard_normal((SRC, SRC), dtype=np.float32) * 8.0), 0, 255).astype(np.uint8)
+    bw, bh = rng.uniform(147, 250, n), rng.uniform(147, 250, n)
+    cx, cy = 225 + rng.uniform(-40, 40, n), 225 + rng.uniform(-40, 40, n)
+    roi = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], -1).astype(np.float32)
+    coord = np.stack([cx, cy, 0.5 * np.maximum(bw, bh)], -1).astype(np.float32)
+    q = rng.standard_normal((n, 4))
+    pose = (q / np.linalg.norm(q, axis=-1, keepdims=True)).astype(np.float32)
+    pts = np.empty((n, 68, 3), np.float32)
+    pts[..., 0] = rng.uniform(roi[:, None, 0], roi[:, None, 2], (n, 68))
+    pts[..., 1] = rng.uniform(roi[:, None, 1], roi[:, None, 3], (n, 68))
+    pts[..., 2] = rng.normal(0, 30, (n, 68))
+    return dict(image=img, roi=roi, coord=coord, pose=pose, pt3d_68=pts)
+
+
+def draw_params(seed: int, n: int, sample_offset: int):
+    from oracle import photometric as opho, pipeline as opipe
+
+    rng = np.random.default_rng(seed)
+    return opipe.sample_geo_params(rng, n), opho.sample_photo_params(rng, n, seed=5, sample_offset=sample_offset)
+
+
+def algorithmic_bytes(host, gp) -> int:
+    """view-box pixels inside the frame (1 B each) + float32 output + labels, summed over the batch."""
+    from oracle import geometric as ogeo
+
+    v = ogeo.round_view_roi(ogeo.compute_view_roi(host["roi"], gp.scales, gp.translations)).astype(np.int64)
+    w = np.clip(np.minimum(v[:, 2], SRC) - np.maximum(v[:, 0], 0), 0, None)
+    h = np.clip(np.minimum(v[:, 3], SRC) - np.maximum(v[:, 1], 0), 0, None)
+    return int((w * h).sum() + len(v) * (OUT * OUT * 4 + LABEL_BYTES))
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline (oracle port)
+
+_CPU_WORK = None
+CATS = dict(image="img", roi="roi", coord="xys", pose="q", pt3d_68="pts")
+
+
+def _cpu_init():
+    import cv2
+
+    cv2.setNumThreads(1)  # like the reference's DataLoader workers (pipelines.py:59-69)
+    try:
+        import torch
+
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+
+
+def _cpu_chunk(rng_):
+    lo, hi = rng_
+    from oracle import pipeline as opipe
+    from oracle.geometric import Sample
+
+    host, gp, pp = _CPU_WORK
+    n = len(host["roi"])
+    idx = [i % n for i in range(lo, hi)]
+    samples = [Sample((SRC, SRC), {k: (host[k][i][..., None] if k == "image" else host[k][i]) for k in CATS}, CATS) for i in idx]
+    sel = lambda a: a[idx]  # noqa: E731
+    from oracle.photometric import PhotoParams
+    from oracle.pipeline import GeoParams
+
+    g = GeoParams(sel(gp.scales), sel(gp.angles), sel(gp.translations), sel(gp.do_flip), sel(gp.rot_dir))
+    p = PhotoParams(pp.order, sel(pp.apply), sel(pp.bits), sel(pp.gamma), sel(pp.contrast), sel(pp.brightness),
+                    sel(pp.noise_apply), pp.noise_std, pp.seed, pp.sample_offset + lo, pp.clip)
+    out, _ = opipe.augment_batch(samples, g, p, OUT)
+    return float(out["image"].sum())
+
+
+class CpuPool:
+    """The oracle's full chain (per-sample geometric/label half + photometric half + whiten) on every host core."""
+
+    CHUNK = 8
+
+    def __init__(self, host, gp, pp):
+        import multiprocessing as mp
+
+        global _CPU_WORK
+        _CPU_WORK = (host, gp, pp)
+        self.cores = len(os.sched_getaffinity(0))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
+        self.pool.map(_cpu_chunk, [(i, i + 1) for i in range(self.cores)])  # spin the workers up
+
+    def run(self, n_samples: int) -> float:
+        """Process n_samples (cycling through the batch); returns wall seconds."""
+        tasks = [(lo, min(lo + self.CHUNK, n_samples)) for lo in range(0, n_samples, self.CHUNK)]
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_chunk, tasks, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_cpu_baseline(host, gp, pp, budget_s=12.0):
+    pool = CpuPool(host, gp, pp)
+    t = pool.run(pool.cores * CpuPool.CHUNK)  # calibration
+    rate = pool.cores * CpuPool.CHUNK / t
+    n = int(min(max(rate * budget_s, BATCH), 16 * BATCH) // CpuPool.CHUNK * CpuPool.CHUNK)
+    t = pool.run(n)
+    pool.close()
+    return dict(value=n / t, unit="samples/s", cores=pool.cores, kind="port",
+                sample=f"{n} samples of the workload (batch 0 cycled), oracle/pipeline.py full chain, {pool.cores} single-threaded "
+                       f"processes, {t:.1f} s wall; CPU: {cpu_model_name()}")
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path (oracle port; the Python reference itself cannot travel to the
+    GPU box) with every host core, one step = one 512-sample batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    host = make_host_batch(0)
+    gp, pp = draw_params(100, BATCH, 0)
+    pool = CpuPool(host, gp, pp)
+    for _ in range(max(args.warmup, 1)):
+        pool.run(BATCH)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pool.run(BATCH)
+    dt = time.perf_counter() - t0
+    pool.close()
+    v = BATCH * args.steps / dt
+    cb = dict(value=v, unit="samples/s", cores=pool.cores, kind="port",
+              sample=f"{args.steps} steps x {BATCH} samples, oracle/pipeline.py full chain, {pool.cores} single-threaded processes; "
+                     f"CPU: {cpu_model_name()}")
+    print(json.dumps({
+        "impl": "reference", "metric": "augmented_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": BATCH, "note": "runs on host cores of rank 0 only"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, power) if p >= 0.6 * max(power)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": float(max(power))}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
+    from trackertraincode_b200.datatransformation import FusedPoseAugmentation, _engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    # host data + the CPU baseline first (forking a pool after CUDA is initialised is asking for trouble)
+    hosts = [make_host_batch(1000 * rank + r) for r in range(RING)]
+    params = [draw_params(100 + 1000 * rank + r, BATCH, (rank * RING + r) * BATCH) for r in range(RING)]
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(hosts[0], *params[0])
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cats = {k: FieldCategory(v) for k, v in CATS.items()}
+    flags = N.F_HALF_PIXEL | N.F_FOCUS | N.F_FLIPROT | N.F_NORMALIZE | N.F_PHOTOMETRIC | N.F_WHITEN
+
+    def device_batch(h):
+        return Batch(Metadata((SRC, SRC), BATCH, "bench", None, dict(cats)), {k: torch.from_numpy(v).to(dev) for k, v in h.items()})
+
+    def to_photo(pp):
+        return E.PhotoParams(pp.order, torch.from_numpy(pp.apply), torch.from_numpy(pp.bits), torch.from_numpy(pp.gamma),
+                             torch.from_numpy(pp.contrast), torch.from_numpy(pp.brightness), torch.from_numpy(pp.noise_apply),
+                             pp.noise_std, pp.seed, pp.sample_offset, pp.clip)
+
+    calls = []
+    for h, (gp, pp) in zip(hosts, params):
+        an = torch.from_numpy(gp.angles)
+        geo = E.GeoParams(torch.from_numpy(gp.scales), an, torch.from_numpy(gp.translations), E.host_cos_sin(an))
+        calls.append(E.prepare_fused(device_batch(h), flags=flags, out_size=OUT, geo=geo,
+                                     do_flip=torch.from_numpy(gp.do_flip.astype(np.uint8)), rot_dir=torch.from_numpy(gp.rot_dir),
+                                     photo=to_photo(pp), want_status=True, rowbuf_capacity=args.rowbuf))
+    alg_bytes = float(np.mean([algorithmic_bytes(h, gp) for h, (gp, _) in zip(hosts, params)]))
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- kernel-resident measurement ("value")
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_spin = time.perf_counter()
+    i = 0
+    while i < args.warmup or time.perf_counter() - t_spin < args.spin_s:  # warm-up: >= W steps and long enough for clocks to settle
+        calls[i % RING].launch()
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize(dev)
+    for c in calls:
+        assert not c.result.status.cpu().numpy().any(), "per-sample status reported a problem"
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.steps):
+        calls[s % RING].launch()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * BATCH * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API from pinned host buffers
+    aug = FusedPoseAugmentation(OUT, rotation_aug_angle=30.0, roi_override="original", enable_image_aug=True, device=dev)
+    pinned = []
+    for h in hosts[:2]:
+        pinned.append(Batch(Metadata((SRC, SRC), BATCH, "bench", None, dict(cats)), {k: torch.from_numpy(v).pin_memory() for k, v in h.items()}))
+    label_keys = ("roi", "coord", "pose", "pt3d_68")
+    host_out = {k: torch.empty_like(pinned[0][k]).pin_memory() for k in label_keys}
+    h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    def e2e_step(s):
+        out = aug(pinned[s % 2])
+        for k in label_keys:
+            host_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return out
+
+    e2e_steps = min(args.steps, 40)
+    for s in range(3):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        e2e_step(s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * BATCH * e2e_steps / e2e_s
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except (OSError, KeyError, ValueError):
+            pass
+        kernel_s = ms * 1e-3 / args.steps  # one fused kernel per step, event-timed on the launching stream
+        achieved = alg_bytes / kernel_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": "augmented_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": world * BATCH,
+                       "l2": f"inputs larger than L2: ring of {RING} distinct batches ({RING * BATCH * SRC * SRC / 1e6:.0f} MB of sources)",
+                       "parallelism": f"per-sample sharding over {world} GPU(s), no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "note": "pinned host frames+labels -> FusedPoseAugmentation (host param sampling) -> labels read back"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "fused_augment_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_us": kernel_s * 1e6, "peak_source": peak_src},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rowbuf", type=int, default=0, help="row-buffer capacity per warp slot (bytes), 0 = library default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spin-s", type=float, default=0.6, help="minimum seconds of untimed warm-up launches (clock settling)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,21 @@ class FusedResult:
     status: Optional[torch.Tensor] = None
 
 
+class PreparedCall:
+    """A fully marshalled b200aug_fused_forward call: argument block, output tensors and the inputs it points to.
+    `launch()` enqueues it on the current stream and can be repeated (same inputs -> same outputs), which is what a
+    steady-state loop or a CUDA-graph capture wants."""
+
+    def __init__(self, args, device, result: FusedResult, keep):
+        self.args, self.device, self.result, self._keep = args, device, result, keep
+
+    def launch(self, stream: Optional[int] = None) -> FusedResult:
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(N.lib.b200aug_fused_forward(C.byref(self.args), C.c_void_p(stream)), "b200aug_fused_forward")
+        return self.result
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise N.NativeError(f"{what} must live on a CUDA device (got {t.device}); this path has no CPU implementation")
@@ -142,12 +157,19 @@ class _ImageSource:
         return t
 
 
-def fused_forward(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams] = None,
+def fused_forward(batch: Batch, **kw) -> FusedResult:
+    """Run the stages selected by `flags` on every field of `batch` in one kernel launch; returns a new Batch."""
+    call = prepare_fused(batch, **kw)
+    with torch.cuda.device(call.device):
+        return call.launch()
+
+
+def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams] = None,
                   do_flip: Optional[torch.Tensor] = None, rot_dir: Optional[torch.Tensor] = None,
                   photo: Optional[PhotoParams] = None, roi_variable: str = "roi", landmark_variable: str = "pt3d_68",
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
-                  want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None) -> FusedResult:
-    """Run the stages selected by `flags` on every field of `batch` in one kernel launch; returns a new Batch."""
+                  want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None) -> PreparedCall:
+    """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
     (B,) = meta.prefixshape if batched else (1,)
@@ -278,11 +300,7 @@ def fused_forward(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         status = torch.empty((B,), dtype=torch.int32, device=device)
         args.status_out = status.data_ptr()
 
-    with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        N.check(N.lib.b200aug_fused_forward(C.byref(args), C.c_void_p(stream)), "b200aug_fused_forward")
-
-    # ---- assemble the result
+    # ---- assemble the result (tensors are written when the call is launched)
     new_meta = meta
     for k, o, shape in pending:
         out_data[k] = o.reshape(shape)
@@ -295,7 +313,7 @@ def fused_forward(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     ordered.update((k, v) for k, v in out_data.items() if k not in ordered)
     res = FusedResult(Batch(new_meta, ordered), view_roi, tr, status)
     res._keep = keep  # inputs must outlive the asynchronous launch
-    return res
+    return PreparedCall(args, device, res, keep)
 
 
 def raise_on_status(status: torch.Tensor):
