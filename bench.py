@@ -70,7 +70,23 @@ def draw_params(seed: int, n: int, sample_offset: int):
     from oracle import photometric as opho, pipeline as opipe
 
     rng = np.random.default_rng(seed)
-    return opipe.sample_geo_params(rng, n), opho.sample_photo_params(rng, n, seed=5, sample_offset=sample_offset)
+    gp, pp = opipe.sample_geo_params(rng, n), opho.sample_photo_params(rng, n, seed=5, sample_offset=sample_offset)
+    # experiment switches for kernel work (never set for a reported number): which parts of the workload to drop
+    drop = os.environ.get("B200AUG_BENCH_DROP", "").split(",")
+    if "rot" in drop:
+        gp.angles[:] = 0
+    if "allrot" in drop:
+        gp.angles[:] = np.float32(np.pi / 6)
+    if "photo" in drop:
+        pp.apply[:] = False
+        pp.noise_apply[:] = False
+    if "blur" in drop:
+        pp.apply[:, 5] = False
+    if "eq" in drop:
+        pp.apply[:, 0] = False
+    if "noise" in drop:
+        pp.noise_apply[:] = False
+    return gp, pp
 
 
 def algorithmic_bytes(host, gp) -> int:
@@ -374,7 +390,8 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": world * BATCH,
                        "l2": f"inputs larger than L2: ring of {RING} distinct batches ({RING * BATCH * SRC * SRC / 1e6:.0f} MB of sources)",
-                       "parallelism": f"per-sample sharding over {world} GPU(s), no collective"},
+                       "parallelism": f"per-sample sharding over {world} GPU(s), no collective",
+                       **({"EXPERIMENT_dropped": os.environ["B200AUG_BENCH_DROP"]} if os.environ.get("B200AUG_BENCH_DROP") else {})},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "note": "pinned host frames+labels -> FusedPoseAugmentation (host param sampling) -> labels read back"},

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200AUG_ABI_VERSION 1
+#define B200AUG_ABI_VERSION 2
 
 /* error codes */
 #define B200AUG_OK 0
@@ -42,7 +42,7 @@ extern "C" {
 #define B200AUG_S_OK 0
 #define B200AUG_S_EMPTY_BOX 1     /* view box with non-positive width/height (cv2.resize would throw) */
 #define B200AUG_S_UNSUPPORTED 2   /* INTER_AREA with one axis up-scaling (unreachable from GeneralFocusRoi) */
-#define B200AUG_S_ROWBUF 3        /* source segment needed by 160 output columns exceeds rowbuf_capacity */
+#define B200AUG_S_ROWBUF 3        /* reserved (ABI 1 reported row-buffer overflow; since ABI 2 such samples take the per-pixel path) */
 
 /* field categories: FieldCategory, trackertraincode/datasets/dshdf5pose.py:21-28 */
 #define B200AUG_CAT_GENERAL 0     /* ""    passes through unchanged */
@@ -145,6 +145,8 @@ typedef struct B200AugFusedArgs {
   uint8_t* image_u8_out;        /* [B,1,oh,ow] when F_NORMALIZE is not set */
   float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
   int32_t* status_out;          /* [B] B200AUG_S_* */
+  uint64_t* trace_out;          /* [B,8] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / tables
+                                   built / resample done / end, then %smid, 0, 0 */
 
   B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
 } B200AugFusedArgs;

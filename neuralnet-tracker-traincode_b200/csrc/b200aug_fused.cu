@@ -2,16 +2,17 @@
 //   label transforms -> crop / warp resample (OpenCV-exact) -> flip/rot90 -> normalise -> photometric chain -> whiten
 // reading each source byte once from HBM and writing the float32 crop once.
 //
-// Pixel path (the specification is oracle/cv2_model.py, pinned bit-exact against cv2):
-//   producer   one canvas row at a time into a per-warp shared-memory row buffer
-//                CROP : zero-padded integer crop row (image_geometric_cv2.py:28-44), 16-byte vector loads
-//                WARP : cv2.warpAffine INTER_LINEAR fixed point (1/32 px coordinates, 15-bit weights)
-//   consumer   resizes canvas -> out_w x out_h
-//                AREA      cv2.resize INTER_AREA, float32 horizontal then vertical accumulation in table order
-//                AREA_INT  integer-factor INTER_AREA (box sums)
-//                LINEAR    cv2.resize INTER_LINEAR, 11-bit fixed point
-//                COPY      canvas already has the output size
-//   each warp owns a band of output rows and walks the canvas rows that feed it, so the canvas never exists in memory.
+// Pixel path (the specification is oracle/cv2_model.py, pinned bit-exact against cv2).  The "canvas" is the image
+// cv2.resize sees: the zero-padded integer crop (image_geometric_cv2.py:28-44) or the output of cv2.warpAffine
+// (INTER_LINEAR fixed point: 1/32 px coordinates, 15-bit weights).  It never exists in memory:
+//   fast path  cv2.resize INTER_AREA with a non-integer factor (what training and evaluation produce): each warp owns
+//              a band of output rows and streams the canvas rows that feed it once, in order.  Crop rows inside the
+//              frame are read straight from global memory as aligned 32-bit words (every source byte is requested
+//              once per CTA; neighbouring lanes share sectors); rows on the frame border and warp rows are staged in a
+//              per-warp shared-memory row.  The lane keeps its columns' tap weights in registers (dense, zero padded),
+//              does the float32 horizontal pass and accumulates the vertical pass in table order.
+//   per-pixel  everything else (integer-factor INTER_AREA, INTER_LINEAR up-scaling, plain copy, extreme sizes) goes
+//              through scalar_out_px(), the straight restatement of the model.
 // The uint8 crop lands in a shared-memory tile (flip/rot90 applied by the store address).  The stage-1 photometric
 // ops are point functions of the uint8 value, so they collapse into a 256-entry LUT per sample (equalize's histogram
 // is the uint8 histogram pushed through the LUT prefix); only the 5x5 blur needs neighbours.  The output pass streams
@@ -29,8 +30,12 @@ constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 static_assert(NTHREADS == 256, "thread v owns photometric LUT entry v");
 constexpr int RMAX = 5;            // column rounds (of 32) per group: 160 output columns share one staged segment
-constexpr int ROW_SLOTS = 2;       // staged canvas rows per warp (LINEAR needs two)
-constexpr int DEFAULT_ROWBUF = 1024;
+constexpr int KMAX = 6;            // widest INTER_AREA tap count the register path unrolls (scale factors up to ~5)
+constexpr int ROWBUF_SLACK = 16;   // the word-wise tap fetch may touch up to 11 bytes past the last tap
+constexpr int DT_CAP = 512;        // widest warp canvas with per-column delta tables in shared memory
+constexpr int DEFAULT_ROWBUF = 2304;  // per-warp staging bytes: a ring of up to RING_MAX crop rows in flight (8 x 288)
+constexpr int RING_MAX = 8;
+constexpr int LAB_CAP = 1024;      // floats of label data staged in shared memory while the plan is being built
 
 enum SrcMode { SRC_CROP = 0, SRC_WARP = 1, SRC_PLAIN = 2 };
 enum RsMode { RS_COPY = 0, RS_AREA = 1, RS_AREA_INT = 2, RS_LINEAR = 3 };
@@ -48,8 +53,9 @@ struct Plan {
   float inv_area;
   int do_flip, rot_dir;
   int status;
+  int kx;              // widest horizontal INTER_AREA tap count (filled while the tables are built)
   int has_t2;
-  AffDerived t_half, t1, t2, t3;   // label transforms in pipeline order
+  AffDerived t1, t2, t3;           // label transforms in pipeline order (the half-pixel offset is a constant)
   int flip_parity;                 // number of mirroring transforms is odd -> landmark permutation
   // photometric
   int n_ops;
@@ -64,7 +70,7 @@ struct Plan {
 };
 
 struct SmemLayout {
-  size_t off_tabs, off_tile, off_rowbuf, total;
+  size_t off_tabs, off_tile, off_rowbuf, off_dtab, off_bars, off_lab, total;
   int ntab;
 };
 
@@ -80,7 +86,13 @@ __host__ __device__ inline SmemLayout smem_layout(int ow, int oh, int cap) {
   L.off_tile = o;
   o += ((size_t)ow * oh + 15) & ~size_t(15);
   L.off_rowbuf = o;
-  o += (size_t)NWARPS * ROW_SLOTS * cap;
+  o += (size_t)NWARPS * (cap + ROWBUF_SLACK);
+  L.off_dtab = o;
+  o += (size_t)DT_CAP * sizeof(int2);
+  L.off_bars = o;
+  o += (size_t)NWARPS * RING_MAX * sizeof(uint64_t);
+  L.off_lab = o;
+  o += (size_t)LAB_CAP * sizeof(float);
   L.total = o;
   return L;
 }
@@ -91,11 +103,45 @@ struct KArgs {
 
 __device__ __forceinline__ int rint_d2i(double v) { return __double2int_rn(v); }
 
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- bulk asynchronous copies (TMA engine, 1-D) completing on an mbarrier: source rows stream into shared memory
+// while the warp computes on earlier rows.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// Spin until the phase with the given parity completes (`bar32`: shared-memory address of the mbarrier).  A copy that
+// never lands would hang the GPU, so the wait traps after ~1 s worth of polls instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar32, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar32), "r"(parity)
+        : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void trace_mark(const B200AugFusedArgs& a, int b, int slot) {
+  if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)b * 8 + slot] = globaltimer_ns();
+}
+
 // ------------------------------------------------------------------------------------------------ plan
 
-__device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, float box[4], bool have_box) {
+// Every global load the plan needs is issued up front (one latency instead of a chain of them); the arithmetic follows.
+__device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, const float box[4]) {
   const int ow = a.out_w, oh = a.out_h;
-  P.status = B200AUG_S_OK;
+  const bool focus = a.flags & B200AUG_F_FOCUS, fliprot = a.flags & B200AUG_F_FLIPROT, photo = a.flags & B200AUG_F_PHOTOMETRIC;
+  // ---- loads
   B200AugSrc s;
   if (a.src_table) {
     s = a.src_table[b];
@@ -103,21 +149,52 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, float box[
     s = a.src_uniform;
     s.ptr += (int64_t)b * a.src_stride;
   }
+  const int do_flip = (fliprot && a.do_flip) ? (a.do_flip[b] != 0) : 0;
+  const int rot_dir = (fliprot && a.rot_dir) ? (int)a.rot_dir[b] : 0;
+  float f = 1.f, rx = 0.f, ry = 0.f, angle = 0.f, cs = 1.f, sn = 0.f;
+  if (focus) {
+    f = a.scales[b];
+    rx = a.translations[2 * b];
+    ry = a.translations[2 * b + 1];
+    angle = a.angles ? a.angles[b] : 0.f;
+    if (a.cos_sin) {
+      cs = a.cos_sin[2 * b];
+      sn = a.cos_sin[2 * b + 1];
+    }
+  }
+  uint8_t op_on[B200AUG_NUM_OPS] = {0, 0, 0, 0, 0, 0}, noise_on[B200AUG_NUM_NOISE] = {0, 0, 0, 0};
+  int bits = 8;
+  float gamma = 1.f, contrast = 1.f, brightness = 1.f;
+  if (photo) {
+    const B200AugPhotoParams& pp = a.photo;
+    if (pp.apply)
+#pragma unroll
+      for (int k = 0; k < B200AUG_NUM_OPS; ++k) op_on[k] = pp.apply[(size_t)b * B200AUG_NUM_OPS + k];
+    if (pp.noise_apply)
+#pragma unroll
+      for (int k = 0; k < B200AUG_NUM_NOISE; ++k) noise_on[k] = pp.noise_apply[(size_t)b * B200AUG_NUM_NOISE + k];
+    if (pp.bits) bits = pp.bits[b];
+    if (pp.gamma) gamma = pp.gamma[b];
+    if (pp.contrast) contrast = pp.contrast[b];
+    if (pp.brightness) brightness = pp.brightness[b];
+  }
+
+  // ---- geometry
+  P.status = B200AUG_S_OK;
+  P.kx = 0;
   P.src = s.ptr;
   P.sw = s.width;
   P.sh = s.height;
   P.pitch = s.pitch;
-  P.do_flip = (a.flags & B200AUG_F_FLIPROT) && a.do_flip ? (a.do_flip[b] != 0) : 0;
-  P.rot_dir = (a.flags & B200AUG_F_FLIPROT) && a.rot_dir ? (int)a.rot_dir[b] : 0;
+  P.do_flip = do_flip;
+  P.rot_dir = rot_dir;
 
-  P.t_half = aff_derive(Aff{1.f, 0.f, 0.5f, 0.f, 1.f, 0.5f});
   Aff t1 = aff_identity();
   int W = P.sw, H = P.sh;  // label coordinate frame before normalisation
 
-  if (a.flags & B200AUG_F_FOCUS) {
+  if (focus) {
     // GeneralFocusRoi._compute_view_roi, geometric.py:135-156 (float32 elementwise, op for op)
     float bx0 = box[0], by0 = box[1], bx1 = box[2], by1 = box[3];
-    float f = a.scales[b], rx = a.translations[2 * b], ry = a.translations[2 * b + 1];
     float bw = sub(bx1, bx0), bh = sub(by1, by0);
     float cx = mul(0.5f, add(bx1, bx0)), cy = mul(0.5f, add(by1, by0));
     float size = mul(fmaxf(bw, bh), f);
@@ -137,14 +214,7 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, float box[
     Aff tr_roi = aff_range_remap((float)vx0, (float)vy0, (float)vx1, (float)vy1, 0.f, 0.f, (float)ow, (float)oh);
     Aff nrm = aff_range_remap(0.f, 0.f, (float)ow, (float)oh, -1.f, -1.f, 1.f, 1.f);
     Aff den = aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, (float)ow, (float)oh);
-    float angle = a.angles ? a.angles[b] : 0.f;
-    float cs, sn;
-    if (a.cos_sin) {
-      cs = a.cos_sin[2 * b];
-      sn = a.cos_sin[2 * b + 1];
-    } else {
-      cos_sin_rn(angle, cs, sn);
-    }
+    if (!a.cos_sin) cos_sin_rn(angle, cs, sn);
     Aff rot = Aff{cs, -sn, 0.f, sn, cs, 0.f};
     t1 = aff_compose(aff_compose(aff_compose(den, rot), nrm), tr_roi);
 
@@ -193,11 +263,11 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, float box[
     P.ch = P.sh;
   }
   P.t1 = aff_derive(t1);
-  if (a.tr_out && (a.flags & B200AUG_F_FOCUS)) {
+  if (a.tr_out && focus) {
     float* o = a.tr_out + 6 * (size_t)b;
     o[0] = t1.a00; o[1] = t1.a01; o[2] = t1.a02; o[3] = t1.a10; o[4] = t1.a11; o[5] = t1.a12;
   }
-  if (a.backtransform_out && (a.flags & B200AUG_F_FOCUS)) {
+  if (a.backtransform_out && focus) {
     Aff iv = aff_inv(t1);
     float* o = a.backtransform_out + 6 * (size_t)b;
     o[0] = iv.a00; o[1] = iv.a01; o[2] = iv.a02; o[3] = iv.a10; o[4] = iv.a11; o[5] = iv.a12;
@@ -236,14 +306,14 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, float box[
     float w = (float)W, h = (float)H;
     if (P.rot_dir != 0) {
       t2 = aff_compose(t2, aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, w, h));
-      float cs, sn;
-      cos_sin_rn((float)((double)P.rot_dir * 3.141592653589793 * 0.5), cs, sn);
-      t2 = aff_compose(t2, Aff{cs, -sn, 0.f, sn, cs, 0.f});
+      // float32(cos), float32(sin) of float32(+-pi/2), as torch evaluates them (affine2d.py:46-47)
+      const float c90 = -0x1.777a5cp-25f, s90 = (P.rot_dir > 0) ? 1.f : -1.f;
+      t2 = aff_compose(t2, Aff{c90, -s90, 0.f, s90, c90, 0.f});
       t2 = aff_compose(t2, aff_range_remap(0.f, 0.f, w, h, -1.f, -1.f, 1.f, 1.f));
     }
     if (P.do_flip) t2 = aff_compose(t2, aff_range_remap(0.f, 0.f, w, h, w, 0.f, 0.f, h));
+    P.t2 = aff_derive(t2);
   }
-  P.t2 = aff_derive(t2);
   // normalize_batch label transform, normalization.py:36-40
   P.t3 = aff_derive(aff_range_remap(0.f, 0.f, (float)W, (float)H, -1.f, -1.f, 1.f, 1.f));
   int nflip = (P.t1.det < 0.f) + (P.has_t2 && P.t2.det < 0.f);
@@ -255,23 +325,27 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, float box[
   P.eq_pos = -1;
   P.eq_step0 = 0;
   P.any_noise = 0;
-  if (a.flags & B200AUG_F_PHOTOMETRIC) {
+  if (photo) {
     const B200AugPhotoParams& pp = a.photo;
     for (int k = 0; k < pp.n_order; ++k) {
-      int op = pp.order[k];
-      if (pp.apply[(size_t)b * B200AUG_NUM_OPS + op]) {
+      const int op = pp.order[k];
+      bool on = false;
+#pragma unroll
+      for (int q = 0; q < B200AUG_NUM_OPS; ++q) on = on || (q == op && op_on[q]);
+      if (on) {
         if (op == B200AUG_OP_BLUR) P.blur_pos = P.n_ops;
         if (op == B200AUG_OP_EQUALIZE) P.eq_pos = P.n_ops;
         P.ops[P.n_ops++] = op;
       }
     }
-    P.bits = pp.bits ? pp.bits[b] : 8;
-    P.gamma = pp.gamma ? pp.gamma[b] : 1.f;
-    P.contrast = pp.contrast ? pp.contrast[b] : 1.f;
-    P.brightness_shift = pp.brightness ? sub(pp.brightness[b], 1.f) : 0.f;
-    for (int s = 0; s < B200AUG_NUM_NOISE; ++s) {
-      P.noise_on[s] = pp.noise_apply ? pp.noise_apply[(size_t)b * B200AUG_NUM_NOISE + s] : 0;
-      P.any_noise |= P.noise_on[s];
+    P.bits = bits;
+    P.gamma = gamma;
+    P.contrast = contrast;
+    P.brightness_shift = sub(brightness, 1.f);
+#pragma unroll
+    for (int q = 0; q < B200AUG_NUM_NOISE; ++q) {
+      P.noise_on[q] = noise_on[q];
+      P.any_noise |= noise_on[q];
     }
   }
 }
@@ -289,14 +363,19 @@ __device__ __forceinline__ void transform_item(const AffDerived& d, int category
 }
 
 __device__ void run_item_chain(const Plan& P, uint32_t flags, int category, float* v, int dim) {
-  if ((flags & B200AUG_F_HALF_PIXEL) && (category == B200AUG_CAT_POINTS || category == B200AUG_CAT_XYS))
-    transform_item(P.t_half, category, v, dim);
+  if ((flags & B200AUG_F_HALF_PIXEL) && (category == B200AUG_CAT_POINTS || category == B200AUG_CAT_XYS)) {
+    // offset_points_by_half_pixel: the affine [[1,0,.5],[0,1,.5]] has det = scales = 1, so only x and y move
+    v[0] = add(v[0], 0.5f);
+    v[1] = add(v[1], 0.5f);
+  }
   if (flags & B200AUG_F_FOCUS) transform_item(P.t1, category, v, dim);
   if ((flags & B200AUG_F_FLIPROT) && P.has_t2) transform_item(P.t2, category, v, dim);
   if (flags & B200AUG_F_NORMALIZE) transform_item(P.t3, category, v, dim);
 }
 
-__device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b) {
+// `staged`: the transformable fields of this sample, packed in field order in shared memory (or NULL)
+__device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b, const float* staged) {
+  int off = 0;
   for (int f = 0; f < a.n_fields; ++f) {
     const B200AugField& F = a.fields[f];
     if (!F.out || !F.in) continue;
@@ -307,6 +386,10 @@ __device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b
       if (in != out)
         for (int i = threadIdx.x; i < cnt * dim; i += NTHREADS) out[i] = in[i];
       continue;
+    }
+    if (staged) {
+      in = staged + off;
+      off += cnt * dim;
     }
     const bool is_roi_from_lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && f == a.roi_field;
     if (is_roi_from_lm) continue;  // written by warp 0 in the prologue
@@ -322,12 +405,12 @@ __device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b
 }
 
 // PutRoiFromLandmarks (batch/misc.py:22-25): [min_xy, max_xy] over the landmarks, by one warp.
-__device__ void landmark_box(const float* pts, int cnt, int dim, const AffDerived* pre, const AffDerived* tr, float box[4]) {
+__device__ void landmark_box(const float* pts, int cnt, int dim, bool half_pixel, const AffDerived* tr, float box[4]) {
   const int lane = threadIdx.x & 31;
   float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
   for (int i = lane; i < cnt; i += 32) {
     float v[3] = {pts[i * dim], pts[i * dim + 1], 0.f};
-    if (pre) tf_point(*pre, v, 2);
+    if (half_pixel) { v[0] = add(v[0], 0.5f); v[1] = add(v[1], 0.5f); }
     if (tr) tf_point(*tr, v, 2);
     mnx = fminf(mnx, v[0]); mny = fminf(mny, v[1]);
     mxx = fmaxf(mxx, v[0]); mxy = fmaxf(mxy, v[1]);
@@ -389,78 +472,327 @@ __device__ void linear_tab_entry(int d, double scale, int ssize, bool is_x, int&
   w1 = (int)rintf(__fmul_rn(f, 2048.f));
 }
 
-// ------------------------------------------------------------------------------------------------ row producers
+// ------------------------------------------------------------------------------------------------ canvas
 
-// Stage canvas row `y`, columns [lo, hi), into `buf`; returns the byte offset of column `lo` inside buf.
-__device__ __forceinline__ int produce_row(const Plan& P, int y, int lo, int hi, uint8_t* buf, int lane) {
-  if (P.src_mode != SRC_WARP) {
-    const int sy = P.y0 + y;
-    const int sx_lo = P.x0 + lo, sx_hi = P.x0 + hi;
-    const bool row_in = (sy >= 0) && (sy < P.sh);
-    if (row_in && sx_lo >= 0 && sx_hi <= P.sw) {
-      const uint8_t* g = P.src + (size_t)sy * P.pitch + sx_lo;
-      const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
-      const uint8_t* g0 = reinterpret_cast<const uint8_t*>(ga & ~uintptr_t(15));
-      const int shift = (int)(ga & 15);
-      const int nvec = (shift + (hi - lo) + 15) >> 4;
-      // stay inside the image allocation (the last row's tail is the only place a 16-byte load could leave it)
-      const uint8_t* img_end = P.src + (size_t)(P.sh - 1) * P.pitch + P.sw;
-      if (g0 >= P.src && g0 + (size_t)nvec * 16 <= img_end) {
-        for (int v = lane; v < nvec; v += 32) {
-          uint4 q = __ldg(reinterpret_cast<const uint4*>(g0) + v);
-          reinterpret_cast<uint4*>(buf)[v] = q;
-        }
-        return shift;
-      }
-      for (int i = lane; i < hi - lo; i += 32) buf[i] = __ldg(g + i);
-      return 0;
-    }
-    for (int i = lane; i < hi - lo; i += 32) {
-      int sx = sx_lo + i;
-      buf[i] = (row_in && sx >= 0 && sx < P.sw) ? __ldg(P.src + (size_t)sy * P.pitch + sx) : (uint8_t)0;
-    }
-    return 0;
-  }
-  // cv2.warpAffine INTER_LINEAR / BORDER_CONSTANT(0), oracle/cv2_model.py:warp_affine_linear_u8
-  const int X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[1], (double)y), P.mi[2]), 1024.0)) + 16;
-  const int Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[4], (double)y), P.mi[5]), 1024.0)) + 16;
-  for (int i = lane; i < hi - lo; i += 32) {
-    const double xd = (double)(lo + i);
-    const int ad = rint_d2i(__dmul_rn(__dmul_rn(P.mi[0], xd), 1024.0));
-    const int bd = rint_d2i(__dmul_rn(__dmul_rn(P.mi[3], xd), 1024.0));
-    const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
-    const int ix = X >> 5, iy = Y >> 5, fx = X & 31, fy = Y & 31;
-    const bool r0 = (iy >= 0) && (iy < P.sh), r1 = (iy + 1 >= 0) && (iy + 1 < P.sh);
-    const bool c0 = (ix >= 0) && (ix < P.sw), c1 = (ix + 1 >= 0) && (ix + 1 < P.sw);
-    const uint8_t* p = P.src + (ptrdiff_t)iy * P.pitch + ix;
-    const int p00 = (r0 && c0) ? __ldg(p) : 0;
-    const int p01 = (r0 && c1) ? __ldg(p + 1) : 0;
-    const int p10 = (r1 && c0) ? __ldg(p + P.pitch) : 0;
-    const int p11 = (r1 && c1) ? __ldg(p + P.pitch + 1) : 0;
-    const int top = (32 - fx) * p00 + fx * p01;
-    const int bot = (32 - fx) * p10 + fx * p11;
-    buf[i] = (uint8_t)(((32 - fy) * top + fy * bot + 512) >> 10);
-  }
-  return 0;
+// One canvas pixel, scalar: the zero-padded crop (image_geometric_cv2.py:28-44) or cv2.warpAffine INTER_LINEAR /
+// BORDER_CONSTANT(0) in fixed point (oracle/cv2_model.py:warp_affine_linear_u8).  This is the specification every
+// fast path below must reproduce; the per-pixel fallback calls it directly.
+__device__ __forceinline__ int bilinear_q5(int p00, int p01, int p10, int p11, int fx, int fy) {
+  const int top = (32 - fx) * p00 + fx * p01;
+  const int bot = (32 - fx) * p10 + fx * p11;
+  return ((32 - fy) * top + fy * bot + 512) >> 10;
 }
 
-// ------------------------------------------------------------------------------------------------ the kernel
-
-__device__ __forceinline__ int tile_index(const Plan& P, int ow, int oh, int dy, int dx) {
-  // geometric.py:256-264: flip(-1), then swapaxes + flip for the 90-degree rotations
-  int x1 = P.do_flip ? (ow - 1 - dx) : dx;
-  int y1 = dy;
-  int x, y;
-  if (P.rot_dir == 0) { x = x1; y = y1; }
-  else if (P.rot_dir == 1) { x = ow - 1 - y1; y = x1; }
-  else { x = y1; y = oh - 1 - x1; }
-  return y * ow + x;
+__device__ int canvas_px(const Plan& P, int x, int y) {
+  if (P.src_mode != SRC_WARP) {
+    const int sx = P.x0 + x, sy = P.y0 + y;
+    return (sx >= 0 && sx < P.sw && sy >= 0 && sy < P.sh) ? (int)__ldg(P.src + (size_t)sy * P.pitch + sx) : 0;
+  }
+  const int X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[1], (double)y), P.mi[2]), 1024.0)) + 16;
+  const int Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[4], (double)y), P.mi[5]), 1024.0)) + 16;
+  const int ad = rint_d2i(__dmul_rn(__dmul_rn(P.mi[0], (double)x), 1024.0));
+  const int bd = rint_d2i(__dmul_rn(__dmul_rn(P.mi[3], (double)x), 1024.0));
+  const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+  const int ix = X >> 5, iy = Y >> 5, fx = X & 31, fy = Y & 31;
+  const bool r0 = (iy >= 0) && (iy < P.sh), r1 = (iy + 1 >= 0) && (iy + 1 < P.sh);
+  const bool c0 = (ix >= 0) && (ix < P.sw), c1 = (ix + 1 >= 0) && (ix + 1 < P.sw);
+  const uint8_t* p = P.src + (ptrdiff_t)iy * P.pitch + ix;
+  const int p00 = (r0 && c0) ? __ldg(p) : 0;
+  const int p01 = (r0 && c1) ? __ldg(p + 1) : 0;
+  const int p10 = (r1 && c0) ? __ldg(p + P.pitch) : 0;
+  const int p11 = (r1 && c1) ? __ldg(p + P.pitch + 1) : 0;
+  return bilinear_q5(p00, p01, p10, p11, fx, fy);
 }
 
 __device__ __forceinline__ uint8_t sat_u8_rint(float v) {
   int r = __float2int_rn(v);
   return (uint8_t)min(max(r, 0), 255);
 }
+
+__device__ __forceinline__ float area_alpha(int t, int n, bool hf, bool hl, float af, float am, float al) {
+  return (t == 0 && hf) ? af : ((t == n - 1 && hl) ? al : am);
+}
+
+// One output pixel of the resize, scalar, for every resampler (the fallback path and the reference semantics of the
+// fast path): cv2.resize INTER_AREA (general + integer factor), INTER_LINEAR, or a plain copy.
+__device__ uint8_t scalar_out_px(const Plan& P, const Tabs& T, int ow, int dx, int dy) {
+  switch (P.rs_mode) {
+    case RS_AREA: {
+      const int xs = T.start[dx], xnf = T.n[dx], xn = xnf & 0xffff;
+      const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
+      const float xaf = T.a[dx], xam = T.b[dx], xal = T.c[dx];
+      const int ys = T.start[ow + dy], ynf = T.n[ow + dy], yn = ynf & 0xffff;
+      const bool yhf = ynf & (1 << 30), yhl = ynf & (1u << 31);
+      const float yaf = T.a[ow + dy], yam = T.b[ow + dy], yal = T.c[ow + dy];
+      float acc = 0.f;
+      for (int k = 0; k < yn; ++k) {
+        float h = 0.f;
+        for (int t = 0; t < xn; ++t)
+          h = __fadd_rn(h, __fmul_rn((float)canvas_px(P, xs + t, ys + k), area_alpha(t, xn, xhf, xhl, xaf, xam, xal)));
+        const float beta = area_alpha(k, yn, yhf, yhl, yaf, yam, yal);
+        acc = (k == 0) ? __fmul_rn(beta, h) : __fadd_rn(acc, __fmul_rn(beta, h));
+      }
+      return sat_u8_rint(acc);
+    }
+    case RS_AREA_INT: {
+      int acc = 0;
+      for (int k = 0; k < P.iscale_y; ++k)
+        for (int t = 0; t < P.iscale_x; ++t) acc += canvas_px(P, dx * P.iscale_x + t, dy * P.iscale_y + k);
+      return (P.iscale_x == 2 && P.iscale_y == 2) ? (uint8_t)((acc + 2) >> 2) : sat_u8_rint(__fmul_rn((float)acc, P.inv_area));
+    }
+    case RS_LINEAR: {
+      const int x0 = T.start[dx], x1 = T.n[dx];
+      const int a0 = __float_as_int(T.a[dx]), a1 = __float_as_int(T.b[dx]);
+      const int r0 = T.start[ow + dy], r1 = T.n[ow + dy];
+      const int b0 = __float_as_int(T.a[ow + dy]), b1 = __float_as_int(T.b[ow + dy]);
+      const int h0 = canvas_px(P, x0, r0) * a0 + canvas_px(P, x1, r0) * a1;
+      const int h1 = canvas_px(P, x0, r1) * a0 + canvas_px(P, x1, r1) * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      return (uint8_t)min(max(v, 0), 255);
+    }
+    default: return (uint8_t)canvas_px(P, dx, dy);  // RS_COPY
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ row staging (shared memory)
+
+// Zero-padded crop row `y` of the canvas, columns [lo, hi), into `buf` (used for rows that touch the image border;
+// interior rows are read straight from global memory by the horizontal pass).  Returns the offset of column `lo`.
+__device__ __forceinline__ int stage_crop_row(const Plan& P, int y, int lo, int hi, uint8_t* buf, int lane) {
+  const int sy = P.y0 + y;
+  const int sx_lo = P.x0 + lo;
+  const bool row_in = (sy >= 0) && (sy < P.sh);
+  for (int i = lane; i < hi - lo; i += 32) {
+    const int sx = sx_lo + i;
+    buf[i] = (row_in && sx >= 0 && sx < P.sw) ? __ldg(P.src + (size_t)sy * P.pitch + sx) : (uint8_t)0;
+  }
+  return 0;
+}
+
+// Canvas row `y` of the warp, columns [lo, hi), into `buf`.  dtab[x] = (adelta, bdelta) of cv2's per-column tables.
+// Rows whose two end points map inside the source (all four taps valid; the map is monotone along the row) skip the
+// border predicates.
+__device__ __forceinline__ void stage_warp_row(const Plan& P, const int2* __restrict__ dtab, int y, int lo, int hi,
+                                               uint8_t* buf, int lane) {
+  const int X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[1], (double)y), P.mi[2]), 1024.0)) + 16;
+  const int Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[4], (double)y), P.mi[5]), 1024.0)) + 16;
+  const int2 da = dtab[lo], db = dtab[hi - 1];
+  const int ixa = (X0 + da.x) >> 10, ixb = (X0 + db.x) >> 10, iya = (Y0 + da.y) >> 10, iyb = (Y0 + db.y) >> 10;
+  const bool interior = min(ixa, ixb) >= 0 && max(ixa, ixb) + 1 < P.sw && min(iya, iyb) >= 0 && max(iya, iyb) + 1 < P.sh;
+  const int pitch = P.pitch;
+  const uint8_t* __restrict__ src = P.src;
+  if (interior) {
+#pragma unroll 4
+    for (int i = lane; i < hi - lo; i += 32) {
+      const int2 d = dtab[lo + i];
+      const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
+      const uint8_t* p = src + (X >> 5) + (Y >> 5) * pitch;
+      buf[i] = (uint8_t)bilinear_q5(__ldg(p), __ldg(p + 1), __ldg(p + pitch), __ldg(p + pitch + 1), X & 31, Y & 31);
+    }
+  } else {
+    const int sw = P.sw, sh = P.sh;
+    for (int i = lane; i < hi - lo; i += 32) {
+      const int2 d = dtab[lo + i];
+      const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
+      const int ix = X >> 5, iy = Y >> 5;
+      const bool r0 = (unsigned)iy < (unsigned)sh, r1 = (unsigned)(iy + 1) < (unsigned)sh;
+      const bool c0 = (unsigned)ix < (unsigned)sw, c1 = (unsigned)(ix + 1) < (unsigned)sw;
+      const uint8_t* p = src + (ptrdiff_t)iy * pitch + ix;
+      const int p00 = (r0 && c0) ? __ldg(p) : 0;
+      const int p01 = (r0 && c1) ? __ldg(p + 1) : 0;
+      const int p10 = (r1 && c0) ? __ldg(p + pitch) : 0;
+      const int p11 = (r1 && c1) ? __ldg(p + pitch + 1) : 0;
+      buf[i] = (uint8_t)bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ INTER_AREA fast path
+
+// Horizontal pass of one staged canvas row for the lane's columns: h[j] = sum_t w[j][t] * S[xoff[j] + t], taps in table
+// order, float32 unfused -- padded taps have weight +0 and leave the sum unchanged.  `base32` is the shared-memory
+// address of canvas column 0 of the row.
+template <int K>
+__device__ __forceinline__ void hrow(uint32_t base32, const int (&xoff)[RMAX], const float (&w)[RMAX][K], float (&h)[RMAX]) {
+  uint32_t px[RMAX][K];
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    const uint32_t a = base32 + (uint32_t)xoff[j];
+#pragma unroll
+    for (int t = 0; t < K; ++t) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(px[j][t]) : "r"(a + t) : "memory");
+  }
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    float s = __fmul_rn(__uint2float_rn(px[j][0]), w[j][0]);
+#pragma unroll
+    for (int t = 1; t < K; ++t) s = __fadd_rn(s, __fmul_rn(__uint2float_rn(px[j][t]), w[j][t]));
+    h[j] = s;
+  }
+}
+
+__device__ __forceinline__ uint32_t cvt_rni_sat_u8(float v) {
+  uint32_t r;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+struct TileMap {  // tile index of output pixel (dy, dx) = o + dy * sa + dx * sb (flip / rot90 folded in)
+  int o, sa, sb;
+};
+
+// geometric.py:256-264: flip(-1), then swapaxes + flip for the 90-degree rotations
+__device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) {
+  TileMap m;
+  if (P.rot_dir == 0) { m.o = 0; m.sa = ow; m.sb = 1; }
+  else if (P.rot_dir == 1) { m.o = ow - 1; m.sa = -1; m.sb = ow; }
+  else { m.o = (oh - 1) * ow; m.sa = 1; m.sb = -ow; }
+  if (P.do_flip) { m.o += (ow - 1) * m.sb; m.sb = -m.sb; }
+  return m;
+}
+
+// cv2.resize INTER_AREA, general (non-integer) factor: each warp owns a band of output rows and streams the canvas
+// rows that feed it exactly once, in order.  Per canvas row: horizontal pass for the lane's columns (registers hold
+// the column taps), then the vertical accumulation in source-row order; a row shared by two output rows (fractional
+// boundary) is used for both.
+// Crop rows inside the frame stream through a per-warp ring of D slots: lane 0 keeps D bulk copies (16-byte aligned
+// supersets of the row segment) in flight, each completing on its slot's mbarrier.  Rows on the frame border are
+// staged synchronously (zero padded), rows outside the frame are zero, warp rows are computed into the staging row.
+template <int K, bool is_warp>
+__device__ __noinline__ void area_band(const Plan& P, const Tabs& T, const TileMap tm, uint8_t* tile, uint8_t* rowbuf, uint64_t* bars,
+                          int cap, const int2* dtab, int ow, int oh, int warp, int lane) {
+  const int dy_begin = (warp * oh) / NWARPS, dy_end = ((warp + 1) * oh) / NWARPS;
+  if (dy_begin >= dy_end) return;
+  // plan fields used per row live in registers (the tile stores would otherwise force reloads from shared memory)
+  const uint8_t* const src = P.src;
+  const int pitch = P.pitch, x0 = P.x0, y0 = P.y0, sw = P.sw, sh = P.sh, cw = P.cw;
+  // canvas columns [cfl, cfh) lie inside the frame; taps outside read zeros (BORDER_CONSTANT / zero padding), which is
+  // the same as giving them weight +0 -- so only the in-frame part of a row is ever fetched
+  const int cfl = is_warp ? 0 : max(0, -x0), cfh = is_warp ? cw : min(cw, sw - x0);
+  const uint32_t rowbuf32 = smem_u32(rowbuf), bars32 = smem_u32(bars);
+  uint32_t parity = 0;  // bit s: phase parity the next wait on ring slot s expects
+  for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
+    const int gcols = min(32 * RMAX, ow - g0);
+    const int glast = g0 + gcols - 1;
+    int xoff[RMAX], tcol[RMAX];
+    float w[RMAX][K];
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      const int dx = g0 + 32 * j + lane;
+      const bool valid = dx <= glast;
+      const int dxc = valid ? dx : g0;
+      const int xnf = T.n[dxc], xn = xnf & 0xffff;
+      const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
+      const float xaf = T.a[dxc], xam = T.b[dxc], xal = T.c[dxc];
+      xoff[j] = T.start[dxc];
+      tcol[j] = valid ? tm.o + dx * tm.sb : -1;
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const int col = xoff[j] + t;
+        w[j][t] = (valid && t < xn && col >= cfl && col < cfh) ? area_alpha(t, xn, xhf, xhl, xaf, xam, xal) : 0.f;
+      }
+    }
+    const int seg_lo = max(T.start[g0], cfl);
+    const int seg_hi = max(min(T.start[glast] + (T.n[glast] & 0xffff), cfh), seg_lo);
+    const int seg_bytes = seg_hi - seg_lo;
+    const int slot_bytes = (seg_bytes + 15 + 15 + ROWBUF_SLACK) & ~15;
+    const int D = max(1, min(RING_MAX, (cap + ROWBUF_SLACK) / slot_bytes));
+
+    const int last = dy_end - 1;
+    const int R0 = T.start[ow + dy_begin];
+    const int R1 = T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
+    // rows [f_lo, f_hi] are read by bulk copies
+    int f_lo = INT_MAX, f_hi = INT_MIN;
+    if (!is_warp && seg_bytes > 0) {
+      const bool last_ok = x0 + seg_hi + 16 <= sw;  // the 16-byte-granular copy of the frame's last row stays inside it
+      f_lo = max(R0, -y0);
+      f_hi = min(R1, (last_ok ? sh - 1 : sh - 2) - y0);
+    }
+    int dy = dy_begin, k = 0;
+    int ys = T.start[ow + dy], ynf = T.n[ow + dy];
+    float yaf = T.a[ow + dy], yam = T.b[ow + dy], yal = T.c[ow + dy];
+    float acc[RMAX];
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) acc[j] = 0.f;
+
+    // ring state of row r: slot index, its shared address, the global address of the row's segment
+    int s = 0;
+    uint32_t slot32 = rowbuf32;
+    uintptr_t ga = reinterpret_cast<uintptr_t>(src) + (ptrdiff_t)(y0 + R0) * pitch + (x0 + seg_lo);
+    auto issue = [&](int slot, uintptr_t g) {  // one lane
+      const uint32_t shift = (uint32_t)(g & 15), bytes = (shift + (uint32_t)seg_bytes + 15u) & ~15u;
+      const uint32_t bar = bars32 + 8u * slot, dst = rowbuf32 + (uint32_t)(slot * slot_bytes);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(g - shift), "r"(bytes), "r"(bar)
+                   : "memory");
+    };
+    __syncwarp();
+    if (lane == 0 && f_lo <= f_hi) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int i = 0; i < D; ++i)
+        if (R0 + i >= f_lo && R0 + i <= f_hi) issue(i, ga + (ptrdiff_t)i * pitch);
+    }
+
+    for (int r = R0; r <= R1; ++r) {
+      float h[RMAX];
+      const int sy = y0 + r;
+      bool zero_row = false;
+      if (is_warp) {
+        __syncwarp();
+        stage_warp_row(P, dtab, r, seg_lo, seg_hi, rowbuf, lane);
+        __syncwarp();
+        hrow<K>(rowbuf32 - seg_lo, xoff, w, h);
+      } else if (is_warp) {  // (compile-time split: the branches below are the crop variant)
+      } else if (r >= f_lo && r <= f_hi) {
+        mbar_wait(bars32 + 8u * s, (parity >> s) & 1u);
+        parity ^= 1u << s;
+        hrow<K>(slot32 + ((uint32_t)ga & 15u) - seg_lo, xoff, w, h);
+      } else if (sy < 0 || sy >= sh) {
+        zero_row = true;
+      } else {  // frame border: zero-padded row staged synchronously in the row's own (idle) slot
+        __syncwarp();
+        stage_crop_row(P, r, seg_lo, seg_hi, rowbuf + s * slot_bytes, lane);
+        __syncwarp();
+        hrow<K>(slot32 - seg_lo, xoff, w, h);
+      }
+      if (zero_row) {
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) h[j] = 0.f;
+      }
+      // vertical pass: this row is tap k of output row dy, and possibly tap 0 of dy + 1 as well
+      while (dy < dy_end && ys + k == r) {
+        const int yn = ynf & 0xffff;
+        const float beta = area_alpha(k, yn, ynf & (1 << 30), ynf & (1u << 31), yaf, yam, yal);
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) acc[j] = (k == 0) ? __fmul_rn(beta, h[j]) : __fadd_rn(acc[j], __fmul_rn(beta, h[j]));
+        if (++k < yn) break;
+        const int trow = dy * tm.sa;
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j)
+          if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)cvt_rni_sat_u8(acc[j]);
+        ++dy;
+        k = 0;
+        if (dy < dy_end) {
+          ys = T.start[ow + dy]; ynf = T.n[ow + dy];
+          yaf = T.a[ow + dy]; yam = T.b[ow + dy]; yal = T.c[ow + dy];
+        }
+      }
+      if (!is_warp) {
+        // the slot of row r is free again: refill it with row r + D
+        __syncwarp();
+        if (lane == 0 && r + D >= f_lo && r + D <= f_hi) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(s, ga + (ptrdiff_t)D * pitch);
+        }
+        ga += pitch;
+        if (++s == D) s = 0;
+        slot32 = rowbuf32 + (uint32_t)(s * slot_bytes);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ photometric helpers
 
 // pointwise stage-1 ops [from, to) of this sample's op list applied to x (oracle/photometric.py)
 __device__ float apply_point_ops(const Plan& P, float x, int from, int to, const float* eq_lut) {
@@ -497,9 +829,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
   return i;
 }
 
-// value of pixel p after the LUT prefix and (if present) the blur: input to the post-blur ops
-__device__ float base_value(const Plan& P, const uint8_t* tile, const float* lut, int ow, int oh, int p) {
-  if (P.blur_pos < 0) return lut[tile[p]];
+// value of pixel p after the LUT prefix and the 5x5 blur: input to the post-blur ops
+__device__ float blurred_value(const uint8_t* tile, const float* lut, int ow, int oh, int p) {
   const int y = p / ow, x = p - y * ow;
   // gaussian_blur2d(5, sigma 1.5), reflect border, horizontal pass then vertical pass (oracle/photometric.py)
   // float32(exp(-t^2/(2 sigma^2))) / float32 sum, identical to oracle/photometric.py:gaussian_kernel1d
@@ -519,7 +850,9 @@ __device__ float base_value(const Plan& P, const uint8_t* tile, const float* lut
   return acc;
 }
 
-__global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_constant__ KArgs K, int cap) {
+// ------------------------------------------------------------------------------------------------ the kernel
+
+__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap) {
   const B200AugFusedArgs& a = K.a;
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x;
@@ -538,28 +871,58 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
   T.b = T.a + L.ntab;
   T.c = T.b + L.ntab;
   uint8_t* tile = smem + L.off_tile;
-  uint8_t* rowbuf = smem + L.off_rowbuf + (size_t)warp * ROW_SLOTS * cap;
+  uint8_t* rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
+  int2* dtab = reinterpret_cast<int2*>(smem + L.off_dtab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
+  float* lab = reinterpret_cast<float*>(smem + L.off_lab);
 
+  trace_mark(a, b, 0);
+  if (a.trace_out && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace_out[(size_t)b * 8 + 5] = smid;
+  }
+  if (lane == 0) {
+    for (int s = 0; s < RING_MAX; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- label data of this sample -> shared memory (overlaps the plan; labels do not depend on it) ----------
+  int lab_total = 0;
+  for (int f = 0; f < a.n_fields; ++f) {
+    const B200AugField& F = a.fields[f];
+    if (F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4) lab_total += F.count * F.dim;
+  }
+  const bool lab_staged = lab_total <= LAB_CAP;
+  if (lab_staged) {
+    int off = 0;
+    for (int f = 0; f < a.n_fields; ++f) {
+      const B200AugField& F = a.fields[f];
+      if (!(F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4)) continue;
+      const int n = F.count * F.dim;
+      const float* src = F.in + (size_t)b * n;
+      for (int i = tid; i < n; i += NTHREADS) lab[off + i] = src[i];
+      off += n;
+    }
+  }
   // ---- prologue: warp 0 builds the plan ------------------------------------------------------------------
   if (warp == 0) {
     float box[4] = {0.f, 0.f, 0.f, 0.f};
     const bool lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && a.landmark_field >= 0;
-    const AffDerived half = aff_derive(Aff{1.f, 0.f, 0.5f, 0.f, 1.f, 0.5f});
+    const bool half = a.flags & B200AUG_F_HALF_PIXEL;
     if (lm) {
       const B200AugField& F = a.fields[a.landmark_field];
-      landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, (a.flags & B200AUG_F_HALF_PIXEL) ? &half : nullptr, nullptr, box);
+      landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, half, nullptr, box);
     } else if (a.roi_field >= 0) {
       const float* r = a.fields[a.roi_field].in + 4 * (size_t)b;
       box[0] = r[0]; box[1] = r[1]; box[2] = r[2]; box[3] = r[3];
     }
-    if (lane == 0) build_plan(a, b, P, box, true);
+    if (lane == 0) build_plan(a, b, P, box);
     __syncwarp();
     if (lm && a.roi_field >= 0 && a.fields[a.roi_field].out) {
       // landmarks mode: the roi label is regenerated from the transformed landmarks after the crop (pipelines.py:347-351)
       const B200AugField& F = a.fields[a.landmark_field];
       float nb[4];
-      landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, (a.flags & B200AUG_F_HALF_PIXEL) ? &half : nullptr,
-                   (a.flags & B200AUG_F_FOCUS) ? &P.t1 : nullptr, nb);
+      landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, half, (a.flags & B200AUG_F_FOCUS) ? &P.t1 : nullptr, nb);
       if (lane == 0) {
         if ((a.flags & B200AUG_F_FLIPROT) && P.has_t2) tf_roi(P.t2, nb);
         if (a.flags & B200AUG_F_NORMALIZE) tf_roi(P.t3, nb);
@@ -570,13 +933,14 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
   }
   __syncthreads();
 
+  trace_mark(a, b, 1);
   if (tid == 0 && a.status_out) a.status_out[b] = P.status;
-  transform_labels(a, P, b);
+  transform_labels(a, P, b, lab_staged ? lab : nullptr);
 
   const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
   if (!want_image) return;
 
-  // ---- resize tables ---------------------------------------------------------------------------------------
+  // ---- resize tables, warp column tables ------------------------------------------------------------------
   const int rs = P.rs_mode;
   if (rs == RS_AREA || rs == RS_LINEAR) {
     for (int i = tid; i < ow + oh; i += NTHREADS) {
@@ -588,6 +952,7 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
         int st, nf; float af, am, al;
         area_tab_entry(d, sc, ss, st, nf, af, am, al);
         T.start[i] = st; T.n[i] = nf; T.a[i] = af; T.b[i] = am; T.c[i] = al;
+        if (is_x) atomicMax(&P.kx, nf & 0xffff);
       } else {
         int i0, i1, w0, w1;
         linear_tab_entry(d, sc, ss, is_x, i0, i1, w0, w1);
@@ -595,149 +960,56 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
       }
     }
   }
+  const bool use_dtab = (P.src_mode == SRC_WARP) && (P.cw <= DT_CAP);
+  if (use_dtab) {
+    for (int x = tid; x < P.cw; x += NTHREADS)
+      dtab[x] = make_int2(rint_d2i(__dmul_rn(__dmul_rn(P.mi[0], (double)x), 1024.0)),
+                          rint_d2i(__dmul_rn(__dmul_rn(P.mi[3], (double)x), 1024.0)));
+  }
   if (a.flags & B200AUG_F_PHOTOMETRIC) {
     hist8[tid] = 0;
     binhist[tid] = 0;
   }
   __syncthreads();
 
-  // ---- resample into the uint8 tile: each warp owns a band of output rows --------------------------------
-  const int dy_begin = (warp * oh) / NWARPS, dy_end = ((warp + 1) * oh) / NWARPS;
-  const bool ok = (P.status == B200AUG_S_OK);
-  bool overflow = false;
-  for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
-    const int gcols = min(32 * RMAX, ow - g0);
-    const int glast = g0 + gcols - 1;
-    // canvas columns this group needs (identical for every row)
-    int seg_lo, seg_hi;
-    if (rs == RS_COPY) { seg_lo = g0; seg_hi = g0 + gcols; }
-    else if (rs == RS_AREA) { seg_lo = T.start[g0]; seg_hi = T.start[glast] + (T.n[glast] & 0xffff); }
-    else if (rs == RS_AREA_INT) { seg_lo = g0 * P.iscale_x; seg_hi = (g0 + gcols) * P.iscale_x; }
-    else { seg_lo = T.start[g0]; seg_hi = T.n[glast] + 1; }
-    if (!ok || seg_hi - seg_lo + 32 > cap) {
-      if (ok) overflow = true;
-      for (int dy = dy_begin; dy < dy_end; ++dy)
-        for (int dx = g0 + lane; dx < g0 + gcols; dx += 32) tile[tile_index(P, ow, oh, dy, dx)] = 0;
-      continue;
+  trace_mark(a, b, 2);
+  // ---- resample into the uint8 tile -----------------------------------------------------------------------
+  const TileMap tm = make_tile_map(P, ow, oh);
+  bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA) && (P.kx <= KMAX) && (P.src_mode != SRC_WARP || use_dtab);
+  if (fast) {
+    // every column group's canvas segment must fit the per-warp row buffer (only staged rows need it)
+    for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
+      const int glast = min(g0 + 32 * RMAX, ow) - 1;
+      if (T.start[glast] + (T.n[glast] & 0xffff) - T.start[g0] + 48 > cap) fast = false;
     }
-    int slot_row[ROW_SLOTS] = {INT_MIN, INT_MIN};
-    int slot_shift[ROW_SLOTS] = {0, 0};
-    float hbuf[RMAX];  // AREA: horizontal pass of the row staged in slot 0
-#pragma unroll
-    for (int j = 0; j < RMAX; ++j) hbuf[j] = 0.f;
-
-    for (int dy = dy_begin; dy < dy_end; ++dy) {
-      if (rs == RS_AREA) {
-        const int ys = T.start[ow + dy], ynf = T.n[ow + dy];
-        const int yn = ynf & 0xffff;
-        const bool yhf = ynf & (1 << 30), yhl = ynf & (1u << 31);
-        const float yaf = T.a[ow + dy], yam = T.b[ow + dy], yal = T.c[ow + dy];
-        float acc[RMAX];
-        for (int k = 0; k < yn; ++k) {
-          const int sy = ys + k;
-          const float beta = (k == 0 && yhf) ? yaf : ((k == yn - 1 && yhl) ? yal : yam);
-          if (slot_row[0] != sy) {
-            __syncwarp();
-            slot_shift[0] = produce_row(P, sy, seg_lo, seg_hi, rowbuf, lane);
-            slot_row[0] = sy;
-            __syncwarp();
-            const uint8_t* S = rowbuf + slot_shift[0] - seg_lo;
-#pragma unroll
-            for (int j = 0; j < RMAX; ++j) {
-              const int dx = g0 + 32 * j + lane;
-              float h = 0.f;
-              if (dx <= glast) {
-                const int xs = T.start[dx], xnf = T.n[dx];
-                const int xn = xnf & 0xffff;
-                const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
-                const float xaf = T.a[dx], xam = T.b[dx], xal = T.c[dx];
-                for (int t = 0; t < xn; ++t) {
-                  const float al = (t == 0 && xhf) ? xaf : ((t == xn - 1 && xhl) ? xal : xam);
-                  h = __fadd_rn(h, __fmul_rn((float)S[xs + t], al));
-                }
-              }
-              hbuf[j] = h;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j)
-            acc[j] = (k == 0) ? __fmul_rn(beta, hbuf[j]) : __fadd_rn(acc[j], __fmul_rn(beta, hbuf[j]));
-        }
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j) {
-          const int dx = g0 + 32 * j + lane;
-          if (dx <= glast) tile[tile_index(P, ow, oh, dy, dx)] = sat_u8_rint(acc[j]);
-        }
-      } else if (rs == RS_COPY) {
-        __syncwarp();
-        const int sh = produce_row(P, dy, seg_lo, seg_hi, rowbuf, lane);
-        __syncwarp();
-        for (int dx = g0 + lane; dx <= glast; dx += 32) tile[tile_index(P, ow, oh, dy, dx)] = rowbuf[sh + dx - seg_lo];
-      } else if (rs == RS_AREA_INT) {
-        int acc[RMAX];
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j) acc[j] = 0;
-        for (int k = 0; k < P.iscale_y; ++k) {
-          __syncwarp();
-          const int sh = produce_row(P, dy * P.iscale_y + k, seg_lo, seg_hi, rowbuf, lane);
-          __syncwarp();
-          const uint8_t* S = rowbuf + sh - seg_lo;
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j) {
-            const int dx = g0 + 32 * j + lane;
-            if (dx <= glast)
-              for (int t = 0; t < P.iscale_x; ++t) acc[j] += S[dx * P.iscale_x + t];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j) {
-          const int dx = g0 + 32 * j + lane;
-          if (dx <= glast) {
-            uint8_t v = (P.iscale_x == 2 && P.iscale_y == 2) ? (uint8_t)((acc[j] + 2) >> 2)
-                                                             : sat_u8_rint(__fmul_rn((float)acc[j], P.inv_area));
-            tile[tile_index(P, ow, oh, dy, dx)] = v;
-          }
-        }
-      } else {  // RS_LINEAR
-        const int r0 = T.start[ow + dy], r1 = T.n[ow + dy];
-        const int b0 = __float_as_int(T.a[ow + dy]), b1 = __float_as_int(T.b[ow + dy]);
-        // keep the two rows in the two slots; rows advance monotonically so reuse whatever is already staged
-        int s0 = (slot_row[0] == r0) ? 0 : ((slot_row[1] == r0) ? 1 : -1);
-        if (s0 < 0) {
-          s0 = (slot_row[0] == r1) ? 1 : 0;
-          __syncwarp();
-          slot_shift[s0] = produce_row(P, r0, seg_lo, seg_hi, rowbuf + s0 * cap, lane);
-          slot_row[s0] = r0;
-        }
-        int s1 = (slot_row[0] == r1) ? 0 : ((slot_row[1] == r1) ? 1 : -1);
-        if (s1 < 0) {
-          s1 = 1 - s0;
-          __syncwarp();
-          slot_shift[s1] = produce_row(P, r1, seg_lo, seg_hi, rowbuf + s1 * cap, lane);
-          slot_row[s1] = r1;
-        }
-        __syncwarp();
-        const uint8_t* S0 = rowbuf + s0 * cap + slot_shift[s0] - seg_lo;
-        const uint8_t* S1 = rowbuf + s1 * cap + slot_shift[s1] - seg_lo;
-        for (int dx = g0 + lane; dx <= glast; dx += 32) {
-          const int x0 = T.start[dx], x1 = T.n[dx];
-          const int a0 = __float_as_int(T.a[dx]), a1 = __float_as_int(T.b[dx]);
-          const int h0 = S0[x0] * a0 + S0[x1] * a1;
-          const int h1 = S1[x0] * a0 + S1[x1] * a1;
-          const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-          tile[tile_index(P, ow, oh, dy, dx)] = (uint8_t)min(max(v, 0), 255);
-        }
-      }
-    }
-    __syncwarp();
   }
-  if (overflow && lane == 0 && a.status_out) a.status_out[b] = B200AUG_S_ROWBUF;
+  if (fast) {
+    const int kx = P.kx;
+#define B200AUG_BAND(KK)                                                                                   \
+  (P.src_mode == SRC_WARP ? area_band<KK, true>(P, T, tm, tile, rowbuf, bars, cap, dtab, ow, oh, warp, lane) \
+                          : area_band<KK, false>(P, T, tm, tile, rowbuf, bars, cap, dtab, ow, oh, warp, lane))
+    if (kx <= 3) B200AUG_BAND(3);
+    else if (kx == 4) B200AUG_BAND(4);
+    else if (kx == 5) B200AUG_BAND(5);
+    else B200AUG_BAND(6);
+#undef B200AUG_BAND
+  } else if (P.status == B200AUG_S_OK) {
+    // per-pixel path: integer-factor area, linear up-scaling, plain copy, very wide taps / canvases
+    for (int p = tid; p < npix; p += NTHREADS) {
+      const int dy = p / ow, dx = p - dy * ow;
+      tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
+    }
+  } else {
+    for (int p = tid; p < npix; p += NTHREADS) tile[p] = 0;
+  }
   __syncthreads();
+  trace_mark(a, b, 3);
 
   // ---- uint8 output (geometric stages only) --------------------------------------------------------------
   if (!(a.flags & B200AUG_F_NORMALIZE)) {
     uint8_t* out = a.image_u8_out + (size_t)b * npix;
     for (int p = tid; p < npix; p += NTHREADS) out[p] = tile[p];
+    trace_mark(a, b, 4);
     return;
   }
 
@@ -795,13 +1067,22 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
   } else {
     xv = apply_point_ops(P, xv, 0, n_pre, eq_lut);
   }
+  const bool whiten = a.flags & B200AUG_F_WHITEN;
+  const bool photo = a.flags & B200AUG_F_PHOTOMETRIC;
+  const bool clip = photo && a.photo.clip;
+  // without blur and noise the rest of the chain is a point function too: fold clip and whiten into the LUT
+  const bool folded = (P.blur_pos < 0) && !P.any_noise;
+  if (folded) {
+    if (clip) xv = fminf(fmaxf(xv, 0.f), 1.f);
+    if (whiten) xv = __fsub_rn(xv, 0.5f);
+  }
   lut[tid] = xv;
   __syncthreads();
 
   if (eq_after_blur) {
     // rare: equalize sits after the blur -> histogram of the blurred (+ intermediate ops) values
     for (int p = tid; p < npix; p += NTHREADS) {
-      float x = base_value(P, tile, lut, ow, oh, p);
+      float x = blurred_value(tile, lut, ow, oh, p);
       x = apply_point_ops(P, x, n_pre + 1, P.eq_pos, eq_lut);
       atomicAdd(&binhist[eq_bin(x)], 1u);
     }
@@ -813,11 +1094,20 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
   // ---- output pass ----------------------------------------------------------------------------------------
   float* out = a.image_f32_out + (size_t)b * npix;
   const int Q = (npix + 3) >> 2;
-  const bool whiten = a.flags & B200AUG_F_WHITEN;
-  const bool photo = a.flags & B200AUG_F_PHOTOMETRIC;
-  const bool clip = photo && a.photo.clip;
+  if (folded) {
+    for (int g = tid; g < Q; g += NTHREADS) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = g + i * Q;
+        if (p < npix) out[p] = lut[tile[p]];
+      }
+    }
+    trace_mark(a, b, 4);
+    return;
+  }
   const uint64_t sid = a.photo.sample_offset + (uint64_t)b;
   const uint2 key = make_uint2((uint32_t)a.photo.seed, (uint32_t)(a.photo.seed >> 32));
+  const bool blur = P.blur_pos >= 0;
   for (int g = tid; g < Q; g += NTHREADS) {
     float x[4];
 #pragma unroll
@@ -825,8 +1115,8 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
       const int p = g + i * Q;
       float v = 0.f;
       if (p < npix) {
-        v = base_value(P, tile, lut, ow, oh, p);
-        if (P.blur_pos >= 0) v = apply_point_ops(P, v, P.blur_pos + 1, P.n_ops, eq_lut);
+        if (blur) v = apply_point_ops(P, blurred_value(tile, lut, ow, oh, p), P.blur_pos + 1, P.n_ops, eq_lut);
+        else v = lut[tile[p]];
       }
       x[i] = v;
     }
@@ -854,6 +1144,7 @@ __global__ void __launch_bounds__(NTHREADS) fused_augment_kernel(const __grid_co
       }
     }
   }
+  trace_mark(a, b, 4);
 }
 
 // ------------------------------------------------------------------------------------------------ apply_affine2d

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200aug.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_FIELDS, NUM_OPS, NUM_NOISE = 8, 6, 4
 
 F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN = 1, 2, 4, 8, 16, 32, 64
@@ -42,6 +42,7 @@ class FusedArgs(C.Structure):
                 ("fields", Field * MAX_FIELDS),
                 ("view_roi_out", C.c_void_p), ("tr_out", C.c_void_p), ("backtransform_out", C.c_void_p),
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),
+                ("trace_out", C.c_void_p),
                 ("photo", PhotoParams)]
 
 

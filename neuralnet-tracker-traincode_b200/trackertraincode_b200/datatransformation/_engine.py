@@ -60,6 +60,7 @@ class FusedResult:
     view_roi: Optional[torch.Tensor] = None
     tr: Optional[torch.Tensor] = None
     status: Optional[torch.Tensor] = None
+    trace: Optional[torch.Tensor] = None
 
 
 class PreparedCall:
@@ -168,7 +169,8 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   do_flip: Optional[torch.Tensor] = None, rot_dir: Optional[torch.Tensor] = None,
                   photo: Optional[PhotoParams] = None, roi_variable: str = "roi", landmark_variable: str = "pt3d_68",
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
-                  want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None) -> PreparedCall:
+                  want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
+                  want_trace: bool = False) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -299,6 +301,10 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     if want_status:
         status = torch.empty((B,), dtype=torch.int32, device=device)
         args.status_out = status.data_ptr()
+    trace = None
+    if want_trace:  # per-CTA timeline (profiling aid, see include/b200aug.h: trace_out)
+        trace = torch.zeros((B, 8), dtype=torch.int64, device=device)
+        args.trace_out = trace.data_ptr()
 
     # ---- assemble the result (tensors are written when the call is launched)
     new_meta = meta
@@ -311,7 +317,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     # keep the reference's key order
     ordered = {k: out_data[k] for k in batch.keys() if k in out_data}
     ordered.update((k, v) for k, v in out_data.items() if k not in ordered)
-    res = FusedResult(Batch(new_meta, ordered), view_roi, tr, status)
+    res = FusedResult(Batch(new_meta, ordered), view_roi, tr, status, trace)
     res._keep = keep  # inputs must outlive the asynchronous launch
     return PreparedCall(args, device, res, keep)
 

@@ -255,9 +255,10 @@ def test_edge_cases(dtr):
         view = ogeo.round_view_roi(ogeo.compute_view_roi(cs[i]["roi"], sc[i], np.zeros(2, np.float32)))
         assert np.array_equal(r.view_roi.cpu().numpy()[i], view)
         assert np.array_equal(img[i], ogeo.croprescale_image(cs[i]["image"], view, (S, S))), f"sample {i}"
-    # tiny row buffer -> per-sample status, not a crash
-    r = E.fused_forward(make_batch(cs), flags=N.F_FOCUS, out_size=S, geo=geo, want_status=True, rowbuf_capacity=64)
-    assert (r.status.cpu().numpy()[2:] == N.S_ROWBUF).all()
+    # tiny row buffer -> the kernel falls back to its per-pixel path: same bits, no error
+    r2 = E.fused_forward(make_batch(cs), flags=N.F_FOCUS, out_size=S, geo=geo, want_status=True, rowbuf_capacity=64)
+    assert not r2.status.cpu().numpy()[1:].any()
+    assert np.array_equal(r2.batch["image"].cpu().numpy(), r.batch["image"].cpu().numpy())
 
 
 def test_nonsquare_output_localizer_shape(dtr):
