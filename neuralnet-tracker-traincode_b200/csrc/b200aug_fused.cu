@@ -54,6 +54,7 @@ struct Plan {
   int do_flip, rot_dir;
   int status;
   int kx;              // widest horizontal INTER_AREA tap count (filled while the tables are built)
+  int fin;             // final rounding of the area sum: 0 rint | 1 integer 2x2 (sum + 2) >> 2 | 2 rint(sum * inv_area)
   int has_t2;
   AffDerived t1, t2, t3;           // label transforms in pipeline order (the half-pixel offset is a constant)
   int flip_parity;                 // number of mirroring transforms is odd -> landmark permutation
@@ -182,6 +183,7 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, const floa
   // ---- geometry
   P.status = B200AUG_S_OK;
   P.kx = 0;
+  P.fin = 0;
   P.src = s.ptr;
   P.sw = s.width;
   P.sh = s.height;
@@ -290,6 +292,7 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, const floa
         bool fast = fabs(P.scale_x - P.iscale_x) < 2.220446049250313e-16 && fabs(P.scale_y - P.iscale_y) < 2.220446049250313e-16;
         P.rs_mode = fast ? RS_AREA_INT : RS_AREA;
         P.inv_area = (float)(1.0 / (double)(P.iscale_x * P.iscale_y));
+        if (fast) P.fin = (P.iscale_x == 2 && P.iscale_y == 2) ? 1 : 2;
       } else {
         P.status = B200AUG_S_UNSUPPORTED;
         P.rs_mode = RS_COPY;
@@ -658,13 +661,29 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 // supersets of the row segment) in flight, each completing on its slot's mbarrier.  Rows on the frame border are
 // staged synchronously (zero padded), rows outside the frame are zero, warp rows are computed into the staging row.
 template <int K, bool is_warp>
-__device__ __noinline__ void area_band(const Plan& P, const Tabs& T, const TileMap tm, uint8_t* tile, uint8_t* rowbuf, uint64_t* bars,
-                          int cap, const int2* dtab, int ow, int oh, int warp, int lane) {
+__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int warp, int lane) {
   const int dy_begin = (warp * oh) / NWARPS, dy_end = ((warp + 1) * oh) / NWARPS;
   if (dy_begin >= dy_end) return;
+  // everything lives in this CTA's dynamic shared memory; deriving the pointers here keeps the address space known
+  // (a generic pointer passed into a non-inlined function turns every table read into a generic load)
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(ow, oh, cap);
+  const Plan& P = *reinterpret_cast<const Plan*>(smem);
+  Tabs T;
+  T.start = reinterpret_cast<int*>(smem + L.off_tabs);
+  T.n = T.start + L.ntab;
+  T.a = reinterpret_cast<float*>(T.n + L.ntab);
+  T.b = T.a + L.ntab;
+  T.c = T.b + L.ntab;
+  uint8_t* const tile = smem + L.off_tile;
+  uint8_t* const rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
+  const int2* const dtab = reinterpret_cast<const int2*>(smem + L.off_dtab);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
   // plan fields used per row live in registers (the tile stores would otherwise force reloads from shared memory)
   const uint8_t* const src = P.src;
   const int pitch = P.pitch, x0 = P.x0, y0 = P.y0, sw = P.sw, sh = P.sh, cw = P.cw;
+  const int fin = P.fin;
+  const float inv_area = P.inv_area;
   // canvas columns [cfl, cfh) lie inside the frame; taps outside read zeros (BORDER_CONSTANT / zero padding), which is
   // the same as giving them weight +0 -- so only the in-frame part of a row is ever fetched
   const int cfl = is_warp ? 0 : max(0, -x0), cfh = is_warp ? cw : min(cw, sw - x0);
@@ -733,6 +752,7 @@ __device__ __noinline__ void area_band(const Plan& P, const Tabs& T, const TileM
         if (R0 + i >= f_lo && R0 + i <= f_hi) issue(i, ga + (ptrdiff_t)i * pitch);
     }
 
+    bool generic_write = false;
     for (int r = R0; r <= R1; ++r) {
       float h[RMAX];
       const int sy = y0 + r;
@@ -754,6 +774,7 @@ __device__ __noinline__ void area_band(const Plan& P, const Tabs& T, const TileM
         stage_crop_row(P, r, seg_lo, seg_hi, rowbuf + s * slot_bytes, lane);
         __syncwarp();
         hrow<K>(slot32 - seg_lo, xoff, w, h);
+        generic_write = true;
       }
       if (zero_row) {
 #pragma unroll
@@ -768,8 +789,13 @@ __device__ __noinline__ void area_band(const Plan& P, const Tabs& T, const TileM
         if (++k < yn) break;
         const int trow = dy * tm.sa;
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j)
-          if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)cvt_rni_sat_u8(acc[j]);
+        for (int j = 0; j < RMAX; ++j) {
+          uint32_t q;
+          if (fin == 0) q = cvt_rni_sat_u8(acc[j]);
+          else if (fin == 1) q = (uint32_t)(((int)acc[j] + 2) >> 2);
+          else q = cvt_rni_sat_u8(__fmul_rn(acc[j], inv_area));
+          if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)q;
+        }
         ++dy;
         k = 0;
         if (dy < dy_end) {
@@ -781,7 +807,9 @@ __device__ __noinline__ void area_band(const Plan& P, const Tabs& T, const TileM
         // the slot of row r is free again: refill it with row r + D
         __syncwarp();
         if (lane == 0 && r + D >= f_lo && r + D <= f_hi) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          // (the slot was last read through the generic proxy; its reads were consumed above.  A slot that was WRITTEN
+          // by generic stores needs the proxy fence before the async engine may overwrite it.)
+          if (generic_write) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           issue(s, ga + (ptrdiff_t)D * pitch);
         }
         ga += pitch;
@@ -942,13 +970,18 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
 
   // ---- resize tables, warp column tables ------------------------------------------------------------------
   const int rs = P.rs_mode;
-  if (rs == RS_AREA || rs == RS_LINEAR) {
+  if (rs == RS_AREA || rs == RS_LINEAR || rs == RS_AREA_INT) {
     for (int i = tid; i < ow + oh; i += NTHREADS) {
       const bool is_x = i < ow;
       const int d = is_x ? i : i - ow;
       const double sc = is_x ? P.scale_x : P.scale_y;
       const int ss = is_x ? P.cw : P.ch;
-      if (rs == RS_AREA) {
+      if (rs == RS_AREA_INT) {
+        // integer factor: plain box sums (unit weights, exact in float32); the rounding happens at the end (Plan::fin)
+        const int isc = is_x ? P.iscale_x : P.iscale_y;
+        T.start[i] = d * isc; T.n[i] = isc; T.a[i] = 0.f; T.b[i] = 1.f; T.c[i] = 0.f;
+        if (is_x) atomicMax(&P.kx, isc);
+      } else if (rs == RS_AREA) {
         int st, nf; float af, am, al;
         area_tab_entry(d, sc, ss, st, nf, af, am, al);
         T.start[i] = st; T.n[i] = nf; T.a[i] = af; T.b[i] = am; T.c[i] = al;
@@ -975,7 +1008,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   trace_mark(a, b, 2);
   // ---- resample into the uint8 tile -----------------------------------------------------------------------
   const TileMap tm = make_tile_map(P, ow, oh);
-  bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA) && (P.kx <= KMAX) && (P.src_mode != SRC_WARP || use_dtab);
+  bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) &&
+              (P.src_mode != SRC_WARP || use_dtab);
   if (fast) {
     // every column group's canvas segment must fit the per-warp row buffer (only staged rows need it)
     for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
@@ -986,8 +1020,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   if (fast) {
     const int kx = P.kx;
 #define B200AUG_BAND(KK)                                                                                   \
-  (P.src_mode == SRC_WARP ? area_band<KK, true>(P, T, tm, tile, rowbuf, bars, cap, dtab, ow, oh, warp, lane) \
-                          : area_band<KK, false>(P, T, tm, tile, rowbuf, bars, cap, dtab, ow, oh, warp, lane))
+  (P.src_mode == SRC_WARP ? area_band<KK, true>(tm, cap, ow, oh, warp, lane) : area_band<KK, false>(tm, cap, ow, oh, warp, lane))
     if (kx <= 3) B200AUG_BAND(3);
     else if (kx == 4) B200AUG_BAND(4);
     else if (kx == 5) B200AUG_BAND(5);

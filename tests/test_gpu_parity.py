@@ -277,3 +277,37 @@ def test_nonsquare_output_localizer_shape(dtr):
         assert np.array_equal(img[i], s.data["image"][0])
         assert_labels(r.batch["roi"][i], s.data["roi"], "roi", atol=2e-4)
         assert_labels(r.batch["pt3d_68"][i], s.data["pt3d_68"], "pt3d_68", atol=2e-4)
+
+
+def test_integer_factor_and_frame_borders(dtr):
+    """Exact 2x / 3x INTER_AREA (cv2's integer box path), crops crossing every frame border, with and without rotation."""
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datatransformation import _engine as E
+
+    rois = [
+        [10, 20, 268, 278],      # 258 -> 129: (a+b+c+d+2)>>2
+        [30, 40, 417, 427],      # 387 -> 129: rint(sum * 1/9)
+        [10, 20, 268, 407],      # 258 x 387: mixed integer factors
+        [-40, 100, 200, 340],    # left border
+        [300, 100, 540, 340],    # right border
+        [100, -60, 340, 180],    # top border
+        [100, 300, 340, 540],    # bottom border (touches the frame's last row)
+        [-30, -30, 480, 480],    # larger than the frame on every side
+        [200, 191, 449, 440],    # right edge exactly at the frame edge, near the last row
+        [0, 0, 450, 450],        # the whole frame
+    ]
+    n = len(rois)
+    cs, rng = random_inputs(n, 31)
+    for c, r in zip(cs, rois):
+        c["roi"] = np.float32(r)
+    for angle in (0.0, float(np.float32(np.pi / 6)), float(np.float32(-0.2))):
+        an = np.full(n, angle, np.float32)
+        geo = E.GeoParams(torch.ones(n), torch.from_numpy(an), torch.zeros(n, 2), host_trig(an))
+        r = E.fused_forward(make_batch(cs), flags=N.F_FOCUS, out_size=S, geo=geo, want_status=True, want_view_roi=True)
+        assert not r.status.cpu().numpy().any()
+        img = r.batch["image"].cpu().numpy()[:, 0]
+        trig = host_trig(an).numpy()
+        for i, c in enumerate(cs):
+            s, inter = ogeo.focus_roi(to_sample(c), ogeo.RoiFocusParams(np.float32(1.0), an[i], np.zeros(2, np.float32), tuple(trig[i])), S)
+            assert np.array_equal(r.view_roi.cpu().numpy()[i], inter["view_roi"])
+            assert np.array_equal(img[i], s.data["image"][0]), f"angle {angle} roi {rois[i]}: {(img[i] != s.data['image'][0]).sum()} pixels differ"
