@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200AUG_ABI_VERSION 2
+#define B200AUG_ABI_VERSION 3
 
 /* error codes */
 #define B200AUG_OK 0
@@ -114,7 +114,7 @@ typedef struct B200AugFusedArgs {
   int32_t batch;
   int32_t out_w, out_h;         /* crop size (129 x 129 for the pose net) */
   uint32_t flags;               /* B200AUG_F_* */
-  int32_t rowbuf_capacity;      /* bytes of staged source row per warp slot; 0 = default (1024) */
+  int32_t rowbuf_capacity;      /* bytes of per-warp staging (ring of source rows in flight); 0 = default (2560) */
 
   /* sources: a table of descriptors (ragged batch) or, if NULL, one descriptor + stride (stacked [B,H,W] tensor) */
   const B200AugSrc* src_table;
@@ -146,7 +146,12 @@ typedef struct B200AugFusedArgs {
   float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
   int32_t* status_out;          /* [B] B200AUG_S_* */
   uint64_t* trace_out;          /* [B,8] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / tables
-                                   built / resample done / end, then %smid, 0, 0 */
+                                   built / resample done / end, then %smid, warp stage done, 0 */
+  /* optional scratch for rotated samples: B regions of workspace_stride bytes (see b200aug_workspace_stride()).  The
+   * two-stage rotated path (warpAffine canvas, then INTER_AREA; image_geometric_cv2.py:121-134) keeps its canvas here,
+   * i.e. in L2.  Without it (NULL) or when a canvas does not fit, canvas rows are produced one at a time instead. */
+  uint8_t* workspace;
+  int64_t workspace_stride;
 
   B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
 } B200AugFusedArgs;
@@ -157,6 +162,8 @@ const char* b200aug_strerror(int code);
 int b200aug_last_cuda_error(void);
 /* dynamic shared memory (bytes) one CTA of the fused kernel uses for this geometry; 0 if it cannot fit */
 size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capacity);
+/* bytes of scratch per sample that hold the rotated canvas of a crop box of up to max_side x max_side source pixels */
+int64_t b200aug_workspace_stride(int max_side);
 
 /* The fused hot path: one launch, one CTA per sample.
  * Replaces, per the flags: batch/normalization.py:83-90, batch/misc.py:9-31, batch/geometric.py:107-231

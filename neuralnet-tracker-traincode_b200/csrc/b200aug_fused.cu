@@ -33,7 +33,8 @@ constexpr int RMAX = 5;            // column rounds (of 32) per group: 160 outpu
 constexpr int KMAX = 6;            // widest INTER_AREA tap count the register path unrolls (scale factors up to ~5)
 constexpr int ROWBUF_SLACK = 16;   // the word-wise tap fetch may touch up to 11 bytes past the last tap
 constexpr int DT_CAP = 512;        // widest warp canvas with per-column delta tables in shared memory
-constexpr int DEFAULT_ROWBUF = 2304;  // per-warp staging bytes: a ring of up to RING_MAX crop rows in flight (8 x 288)
+constexpr int DEFAULT_ROWBUF = 2560;  // per-warp staging bytes: a ring of up to RING_MAX crop rows in flight, or one
+                                      // staged warpAffine tile footprint (39 rows x 64 B)
 constexpr int RING_MAX = 8;
 constexpr int LAB_CAP = 1024;      // floats of label data staged in shared memory while the plan is being built
 
@@ -567,8 +568,8 @@ __device__ __forceinline__ int stage_crop_row(const Plan& P, int y, int lo, int 
   const bool row_in = (sy >= 0) && (sy < P.sh);
   for (int i = lane; i < hi - lo; i += 32) {
     const int sx = sx_lo + i;
-    buf[i] = (row_in && sx >= 0 && sx < P.sw) ? __ldg(P.src + (size_t)sy * P.pitch + sx) : (uint8_t)0;
-  }
+    buf[i] = (row_in && sx >= 0 && sx < P.sw) ? P.src[(size_t)sy * P.pitch + sx] : (uint8_t)0;  // coherent load: the
+  }                                                    // source may be the scratch canvas written earlier in this kernel
   return 0;
 }
 
@@ -608,6 +609,110 @@ __device__ __forceinline__ void stage_warp_row(const Plan& P, const int2* __rest
       buf[i] = (uint8_t)bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ warpAffine, tile-staged
+
+constexpr int WT_W = 32, WT_H = 16;     // canvas tile of one warp iteration
+constexpr int WT_STRIDE = 64;           // staged source row: <= 38 px of bounding box + 15 B alignment shift, in 16 B chunks
+constexpr int WT_ROWS = 39;             // tallest bounding box of a 32 x 16 tile under any rotation at unit scale, + taps
+
+// cv2.warpAffine of the whole canvas into `scratch` (global memory, stays in L2; row pitch `spitch`), one 32 x 16 canvas
+// tile per warp iteration.  The canvas has the resolution of the source (image_geometric_cv2.py:121-124 sizes it so), so a
+// tile's source footprint is a rotated 32 x 16 rectangle: its bounding box (<= 39 rows x 38 px) is staged in the warp's
+// shared-memory area with 16-byte loads and the four bilinear taps of every pixel are gathered from there -- a gather
+// straight from global memory would touch ~16 cache lines per warp instruction.  Tiles whose bounding box leaves the
+// frame (BORDER_CONSTANT zeros) or is too large (a down-scaling canvas never is) take the predicated global path.
+__device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ dtab, uint8_t* stage, int stage_bytes,
+                                       uint8_t* __restrict__ scratch, int spitch, int warp, int lane) {
+  const uint8_t* __restrict__ src = P.src;
+  const int pitch = P.pitch, sw = P.sw, sh = P.sh, cw = P.cw, ch = P.ch;
+  const double m1 = P.mi[1], m2 = P.mi[2], m4 = P.mi[4], m5 = P.mi[5];
+  const int tiles_x = (cw + WT_W - 1) / WT_W, tiles_y = (ch + WT_H - 1) / WT_H;
+  const uint32_t stage32 = smem_u32(stage);
+  const int pm = pitch & 15;
+  auto row_origin = [&](int y, int& X0, int& Y0) {
+    X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
+    Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
+  };
+  for (int t = warp; t < tiles_x * tiles_y; t += NWARPS) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int x_lo = tx * WT_W, y_lo = ty * WT_H;
+    const int tw = min(WT_W, cw - x_lo), th = min(WT_H, ch - y_lo);
+    // bounding box of the taps from the four tile corners (the fixed-point map is monotone in x and in y)
+    int Xa, Ya, Xb, Yb;
+    row_origin(y_lo, Xa, Ya);
+    row_origin(y_lo + th - 1, Xb, Yb);
+    const int2 dl = dtab[x_lo], dr = dtab[x_lo + tw - 1];
+    const int ix0 = (Xa + dl.x) >> 10, ix1 = (Xa + dr.x) >> 10, ix2 = (Xb + dl.x) >> 10, ix3 = (Xb + dr.x) >> 10;
+    const int iy0 = (Ya + dl.y) >> 10, iy1 = (Ya + dr.y) >> 10, iy2 = (Yb + dl.y) >> 10, iy3 = (Yb + dr.y) >> 10;
+    const int bx0 = min(min(ix0, ix1), min(ix2, ix3)), bx1 = max(max(ix0, ix1), max(ix2, ix3)) + 1;
+    const int by0 = min(min(iy0, iy1), min(iy2, iy3)), by1 = max(max(iy0, iy1), max(iy2, iy3)) + 1;
+    const int nrows = by1 - by0 + 1;
+    // staged: inside the frame (and not on its last row: the 16-byte chunks may run past a row's end), small enough
+    const bool staged = bx0 >= 0 && bx1 < sw && by0 >= 0 && by1 < sh - 1 && nrows <= WT_ROWS && (bx1 - bx0 + 1) + 15 <= WT_STRIDE &&
+                        nrows * WT_STRIDE <= stage_bytes;
+    const uintptr_t gbase = reinterpret_cast<uintptr_t>(src) + (size_t)by0 * pitch + bx0;  // top-left of the box
+    __syncwarp();
+    if (staged) {
+      // item = (row, 16-byte chunk); all loads first, then the stores
+      uint4 v[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int item = lane + 32 * i, row = item >> 2, k = item & 3;
+        if (row < nrows) {
+          const uintptr_t g = (gbase + (size_t)row * pitch) & ~uintptr_t(15);
+          v[i] = __ldg(reinterpret_cast<const uint4*>(g) + k);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int item = lane + 32 * i, row = item >> 2, k = item & 3;
+        if (row < nrows) *reinterpret_cast<uint4*>(stage + row * WT_STRIDE + 16 * k) = v[i];
+      }
+      __syncwarp();
+      const int c0 = (int)(gbase & 15);  // alignment shift of box row r: (c0 + r * pm) & 15
+      int X0l, Y0l;                      // lane yy holds the row origin of tile row yy
+      row_origin(y_lo + min(lane, th - 1), X0l, Y0l);
+      const int2 d = dtab[x_lo + min(lane, tw - 1)];
+      uint8_t* out = scratch + (size_t)y_lo * spitch + x_lo + lane;
+#pragma unroll 4
+      for (int yy = 0; yy < th; ++yy) {
+        const int X0 = __shfl_sync(0xffffffffu, X0l, yy), Y0 = __shfl_sync(0xffffffffu, Y0l, yy);
+        if (lane < tw) {
+          const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
+          const int ixr = (X >> 5) - bx0, iyr = (Y >> 5) - by0;
+          const int s0 = (c0 + iyr * pm) & 15, s1 = (s0 + pm) & 15;
+          const uint32_t a0 = stage32 + (uint32_t)(iyr * WT_STRIDE + s0 + ixr), a1 = stage32 + (uint32_t)((iyr + 1) * WT_STRIDE + s1 + ixr);
+          uint32_t p00, p01, p10, p11;
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a0) : "memory");
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p01) : "r"(a0 + 1) : "memory");
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a1) : "memory");
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p11) : "r"(a1 + 1) : "memory");
+          out[(size_t)yy * spitch] = (uint8_t)bilinear_q5((int)p00, (int)p01, (int)p10, (int)p11, X & 31, Y & 31);
+        }
+      }
+    } else if (lane < tw) {
+      const int2 d = dtab[x_lo + lane];
+      uint8_t* out = scratch + (size_t)y_lo * spitch + x_lo + lane;
+      for (int yy = 0; yy < th; ++yy) {
+        int X0, Y0;
+        row_origin(y_lo + yy, X0, Y0);
+        const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
+        const int ix = X >> 5, iy = Y >> 5;
+        const bool r0 = (unsigned)iy < (unsigned)sh, r1 = (unsigned)(iy + 1) < (unsigned)sh;
+        const bool c0 = (unsigned)ix < (unsigned)sw, c1 = (unsigned)(ix + 1) < (unsigned)sw;
+        const uint8_t* p = src + (ptrdiff_t)iy * pitch + ix;
+        const int p00 = (r0 && c0) ? __ldg(p) : 0;
+        const int p01 = (r0 && c1) ? __ldg(p + 1) : 0;
+        const int p10 = (r1 && c0) ? __ldg(p + pitch) : 0;
+        const int p11 = (r1 && c1) ? __ldg(p + pitch + 1) : 0;
+        out[(size_t)yy * spitch] = (uint8_t)bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
+      }
+    }
+  }
+  // the canvas is read back through the async proxy (bulk copies): order these generic-proxy writes before it
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ INTER_AREA fast path
@@ -1006,6 +1111,26 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   __syncthreads();
 
   trace_mark(a, b, 2);
+  // ---- rotated samples, stage 1: warpAffine into this sample's scratch canvas; stage 2 is then a plain crop of it ----
+  if (use_dtab && a.workspace && P.status == B200AUG_S_OK) {
+    const int spitch = (P.cw + 16 + 15) & ~15;  // 16-byte aligned rows with room for the bulk copies' over-read
+    if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
+      uint8_t* scratch = a.workspace + (size_t)b * a.workspace_stride;
+      warp_canvas_to_scratch(P, dtab, rowbuf, cap + ROWBUF_SLACK, scratch, spitch, warp, lane);
+      __syncthreads();
+      if (tid == 0) {
+        P.src = scratch;
+        P.pitch = spitch;
+        P.sw = spitch;  // columns [cw, spitch) are padding the row copies may touch but no tap ever reads
+        P.sh = P.ch + 1;
+        P.x0 = 0;
+        P.y0 = 0;
+        P.src_mode = SRC_CROP;
+      }
+      __syncthreads();
+    }
+  }
+  trace_mark(a, b, 6);
   // ---- resample into the uint8 tile -----------------------------------------------------------------------
   const TileMap tm = make_tile_map(P, ow, oh);
   bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) &&
@@ -1243,6 +1368,12 @@ extern "C" size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capa
   cap = (cap + 15) & ~15;
   size_t t = smem_layout(out_w, out_h, cap).total;
   return t <= 227 * 1024 ? t : 0;
+}
+
+extern "C" int64_t b200aug_workspace_stride(int max_side) {
+  if (max_side <= 0) return 0;
+  const int64_t spitch = (max_side + 16 + 15) & ~15;
+  return ((spitch * (max_side + 1)) + 255) & ~int64_t(255);
 }
 
 static int check_fields(int n, const B200AugField* f) {

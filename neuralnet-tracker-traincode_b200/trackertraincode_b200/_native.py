@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200aug.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_FIELDS, NUM_OPS, NUM_NOISE = 8, 6, 4
 
 F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN = 1, 2, 4, 8, 16, 32, 64
@@ -42,12 +42,12 @@ class FusedArgs(C.Structure):
                 ("fields", Field * MAX_FIELDS),
                 ("view_roi_out", C.c_void_p), ("tr_out", C.c_void_p), ("backtransform_out", C.c_void_p),
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),
-                ("trace_out", C.c_void_p),
+                ("trace_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_stride", C.c_int64),
                 ("photo", PhotoParams)]
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_fused_forward", "b200aug_apply_affine2d")
+           "b200aug_workspace_stride", "b200aug_fused_forward", "b200aug_apply_affine2d")
 
 
 class NativeError(RuntimeError):
@@ -65,6 +65,8 @@ def _load():
     lib.b200aug_last_cuda_error.restype = C.c_int
     lib.b200aug_fused_smem_bytes.restype = C.c_size_t
     lib.b200aug_fused_smem_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.b200aug_workspace_stride.restype = C.c_int64
+    lib.b200aug_workspace_stride.argtypes = [C.c_int]
     lib.b200aug_fused_forward.restype = C.c_int
     lib.b200aug_fused_forward.argtypes = [C.POINTER(FusedArgs), C.c_void_p]
     lib.b200aug_apply_affine2d.restype = C.c_int

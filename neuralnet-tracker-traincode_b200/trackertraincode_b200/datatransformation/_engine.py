@@ -158,6 +158,22 @@ class _ImageSource:
         return t
 
 
+WORKSPACE_SIDE = 512  # widest rotated canvas kept in scratch (larger ones are produced row by row)
+_WORKSPACES: Dict[Any, torch.Tensor] = {}
+
+
+def _workspace(device, B: int):
+    """Scratch for the rotated canvases of one launch (B200AugFusedArgs.workspace): one region per sample, cached per
+    device and grown on demand.  Launches on one stream reuse it safely; concurrent streams must not share it."""
+    stride = int(N.lib.b200aug_workspace_stride(WORKSPACE_SIDE))
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < B * stride:
+        ws = torch.empty(B * stride, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws, stride
+
+
 def fused_forward(batch: Batch, **kw) -> FusedResult:
     """Run the stages selected by `flags` on every field of `batch` in one kernel launch; returns a new Batch."""
     call = prepare_fused(batch, **kw)
@@ -170,7 +186,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   photo: Optional[PhotoParams] = None, roi_variable: str = "roi", landmark_variable: str = "pt3d_68",
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
-                  want_trace: bool = False) -> PreparedCall:
+                  want_trace: bool = False, use_workspace: bool = True) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -289,6 +305,10 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
             args.image_u8_out = img_out.data_ptr()
 
     view_roi = tr = status = None
+    if (flags & N.F_FOCUS) and image_keys and use_workspace:
+        ws, stride = _workspace(device, B)
+        args.workspace, args.workspace_stride = ws.data_ptr(), stride
+        keep.append(ws)
     if flags & N.F_FOCUS:
         if want_view_roi:
             view_roi = torch.empty((B, 4), dtype=torch.int32, device=device)

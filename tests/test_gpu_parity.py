@@ -311,3 +311,29 @@ def test_integer_factor_and_frame_borders(dtr):
             s, inter = ogeo.focus_roi(to_sample(c), ogeo.RoiFocusParams(np.float32(1.0), an[i], np.zeros(2, np.float32), tuple(trig[i])), S)
             assert np.array_equal(r.view_roi.cpu().numpy()[i], inter["view_roi"])
             assert np.array_equal(img[i], s.data["image"][0]), f"angle {angle} roi {rois[i]}: {(img[i] != s.data['image'][0]).sum()} pixels differ"
+
+
+def test_rotated_paths_agree(dtr):
+    """The rotated samples' two implementations (canvas in the L2 scratch workspace vs. canvas rows produced one at a time)
+    and the per-pixel fallback (tiny row buffer) must give identical bits."""
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datatransformation import _engine as E
+
+    n = 48
+    cs, rng = random_inputs(n, 77)
+    gp = opipe.sample_geo_params(rng, n)
+    gp.angles[::2] = np.float32(np.pi / 6) * np.where(np.arange(n)[::2] % 4 == 0, 1, -1)
+    gp.angles[1] = np.float32(0.7)  # more than the training range
+    an = torch.from_numpy(gp.angles)
+    geo = E.GeoParams(torch.from_numpy(gp.scales), an, torch.from_numpy(gp.translations), E.host_cos_sin(an))
+    outs = []
+    for kw in (dict(use_workspace=True), dict(use_workspace=False), dict(use_workspace=True, rowbuf_capacity=64)):
+        r = E.fused_forward(make_batch(cs), flags=N.F_FOCUS, out_size=S, geo=geo, want_status=True, **kw)
+        assert not r.status.cpu().numpy().any()
+        outs.append(r.batch["image"].cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])
+    for i in range(0, n, 6):
+        trig = host_trig(gp.angles[i:i + 1]).numpy()[0]
+        s, _ = ogeo.focus_roi(to_sample(cs[i]), ogeo.RoiFocusParams(gp.scales[i], gp.angles[i], gp.translations[i], tuple(trig)), S)
+        assert np.array_equal(outs[0][i, 0], s.data["image"][0])
