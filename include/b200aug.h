@@ -135,7 +135,7 @@ typedef struct B200AugFusedArgs {
   int32_t n_fields;
   int32_t roi_field;            /* index into fields of the focus box (roi_variable), -1 if F_ROI_FROM_LANDMARKS only */
   int32_t landmark_field;       /* index of pt3d_68 for F_ROI_FROM_LANDMARKS, else -1 */
-  int32_t reserved;
+  int32_t cluster_size;         /* CTAs (thread-block cluster) that share one sample: 1, 2 or 4; 0 = default (2) */
   B200AugField fields[B200AUG_MAX_FIELDS];
 
   /* outputs (each may be NULL) */
@@ -145,7 +145,7 @@ typedef struct B200AugFusedArgs {
   uint8_t* image_u8_out;        /* [B,1,oh,ow] when F_NORMALIZE is not set */
   float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
   int32_t* status_out;          /* [B] B200AUG_S_* */
-  uint64_t* trace_out;          /* [B,8] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / tables
+  uint64_t* trace_out;          /* [B*cluster_size,8] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / tables
                                    built / resample done / end, then %smid, warp stage done, 0 */
   /* optional scratch for rotated samples: B regions of workspace_stride bytes (see b200aug_workspace_stride()).  The
    * two-stage rotated path (warpAffine canvas, then INTER_AREA; image_geometric_cv2.py:121-134) keeps its canvas here,

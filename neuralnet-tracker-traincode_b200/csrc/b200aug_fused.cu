@@ -36,6 +36,7 @@ constexpr int DT_CAP = 512;        // widest warp canvas with per-column delta t
 constexpr int DEFAULT_ROWBUF = 2560;  // per-warp staging bytes: a ring of up to RING_MAX crop rows in flight, or one
                                       // staged warpAffine tile footprint (39 rows x 64 B)
 constexpr int RING_MAX = 8;
+constexpr int DEFAULT_CLUSTER = 2;  // CTAs sharing one sample
 constexpr int LAB_CAP = 1024;      // floats of label data staged in shared memory while the plan is being built
 
 enum SrcMode { SRC_CROP = 0, SRC_WARP = 1, SRC_PLAIN = 2 };
@@ -58,7 +59,6 @@ struct Plan {
   int fin;             // final rounding of the area sum: 0 rint | 1 integer 2x2 (sum + 2) >> 2 | 2 rint(sum * inv_area)
   int has_t2;
   AffDerived t1, t2, t3;           // label transforms in pipeline order (the half-pixel offset is a constant)
-  int flip_parity;                 // number of mirroring transforms is odd -> landmark permutation
   // photometric
   int n_ops;
   int ops[B200AUG_NUM_OPS];
@@ -133,68 +133,85 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar32, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void trace_mark(const B200AugFusedArgs& a, int b, int slot) {
-  if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)b * 8 + slot] = globaltimer_ns();
+__device__ __forceinline__ void trace_mark(const B200AugFusedArgs& a, int slot) {
+  if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)blockIdx.x * 8 + slot] = globaltimer_ns();
+}
+
+// ---- thread-block clusters: the CTAs of a cluster share one sample (each resamples a band of rows and stores the
+// pixels into every CTA's tile through distributed shared memory, then each finishes its share of the output)
+constexpr int MAX_CLUSTER = 4;
+
+__device__ __forceinline__ void cluster_info(uint32_t& rank, uint32_t& size) {
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(size));
+}
+
+// barrier over all threads of the cluster (release/acquire: global and distributed-shared writes before it are visible
+// after it); with a single CTA this is a plain __syncthreads()
+__device__ __forceinline__ void cluster_sync(uint32_t cl) {
+  if (cl > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+
+__device__ __forceinline__ void st_cluster_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ plan
 
-// Every global load the plan needs is issued up front (one latency instead of a chain of them); the arithmetic follows.
-__device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, const float box[4]) {
-  const int ow = a.out_w, oh = a.out_h;
-  const bool focus = a.flags & B200AUG_F_FOCUS, fliprot = a.flags & B200AUG_F_FLIPROT, photo = a.flags & B200AUG_F_PHOTOMETRIC;
-  // ---- loads
+// The plan is built by several warps at once: every warp evaluates the short common chain (view box -> focus transform,
+// redundantly in all lanes, so no exchange is needed) and then one branch each -- warpAffine matrix, resize decision,
+// derived label-transform scalars, flip/rot90 transform, normalisation transform, photometric parameters.  A single
+// lane doing all of it serially costs ~8 us of latency per CTA.
+
+struct PlanCore {
   B200AugSrc s;
+  int do_flip, rot_dir;
+  float angle;
+  Aff t1;            // focus transform (identity without F_FOCUS)
+  int vx0, vy0, vx1, vy1;
+  int src_mode, cw, ch;
+  int W, H;          // label frame before normalisation
+};
+
+__device__ PlanCore plan_core(const B200AugFusedArgs& a, int b, const float box[4]) {
+  const int ow = a.out_w, oh = a.out_h;
+  const bool focus = a.flags & B200AUG_F_FOCUS, fliprot = a.flags & B200AUG_F_FLIPROT;
+  PlanCore c;
+  // ---- loads (issued together)
   if (a.src_table) {
-    s = a.src_table[b];
+    c.s = a.src_table[b];
   } else {
-    s = a.src_uniform;
-    s.ptr += (int64_t)b * a.src_stride;
+    c.s = a.src_uniform;
+    c.s.ptr += (int64_t)b * a.src_stride;
   }
-  const int do_flip = (fliprot && a.do_flip) ? (a.do_flip[b] != 0) : 0;
-  const int rot_dir = (fliprot && a.rot_dir) ? (int)a.rot_dir[b] : 0;
-  float f = 1.f, rx = 0.f, ry = 0.f, angle = 0.f, cs = 1.f, sn = 0.f;
+  c.do_flip = (fliprot && a.do_flip) ? (a.do_flip[b] != 0) : 0;
+  c.rot_dir = (fliprot && a.rot_dir) ? (int)a.rot_dir[b] : 0;
+  float f = 1.f, rx = 0.f, ry = 0.f, cs = 1.f, sn = 0.f;
+  c.angle = 0.f;
   if (focus) {
     f = a.scales[b];
     rx = a.translations[2 * b];
     ry = a.translations[2 * b + 1];
-    angle = a.angles ? a.angles[b] : 0.f;
+    c.angle = a.angles ? a.angles[b] : 0.f;
     if (a.cos_sin) {
       cs = a.cos_sin[2 * b];
       sn = a.cos_sin[2 * b + 1];
     }
   }
-  uint8_t op_on[B200AUG_NUM_OPS] = {0, 0, 0, 0, 0, 0}, noise_on[B200AUG_NUM_NOISE] = {0, 0, 0, 0};
-  int bits = 8;
-  float gamma = 1.f, contrast = 1.f, brightness = 1.f;
-  if (photo) {
-    const B200AugPhotoParams& pp = a.photo;
-    if (pp.apply)
-#pragma unroll
-      for (int k = 0; k < B200AUG_NUM_OPS; ++k) op_on[k] = pp.apply[(size_t)b * B200AUG_NUM_OPS + k];
-    if (pp.noise_apply)
-#pragma unroll
-      for (int k = 0; k < B200AUG_NUM_NOISE; ++k) noise_on[k] = pp.noise_apply[(size_t)b * B200AUG_NUM_NOISE + k];
-    if (pp.bits) bits = pp.bits[b];
-    if (pp.gamma) gamma = pp.gamma[b];
-    if (pp.contrast) contrast = pp.contrast[b];
-    if (pp.brightness) brightness = pp.brightness[b];
-  }
-
-  // ---- geometry
-  P.status = B200AUG_S_OK;
-  P.kx = 0;
-  P.fin = 0;
-  P.src = s.ptr;
-  P.sw = s.width;
-  P.sh = s.height;
-  P.pitch = s.pitch;
-  P.do_flip = do_flip;
-  P.rot_dir = rot_dir;
-
-  Aff t1 = aff_identity();
-  int W = P.sw, H = P.sh;  // label coordinate frame before normalisation
-
+  c.t1 = aff_identity();
+  c.W = c.s.width;
+  c.H = c.s.height;
+  c.vx0 = c.vy0 = c.vx1 = c.vy1 = 0;
   if (focus) {
     // GeneralFocusRoi._compute_view_roi, geometric.py:135-156 (float32 elementwise, op for op)
     float bx0 = box[0], by0 = box[1], bx1 = box[2], by1 = box[3];
@@ -207,85 +224,93 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, const floa
     float tx = mul(wx, rx), ty = mul(wy, ry);
     float hs = mul(size, 0.5f);
     // torch.round (half to even) -> int32, geometric.py:205
-    int vx0 = (int)rintf(add(sub(cx, hs), tx)), vy0 = (int)rintf(add(sub(cy, hs), ty));
-    int vx1 = (int)rintf(add(add(cx, hs), tx)), vy1 = (int)rintf(add(add(cy, hs), ty));
-    if (a.view_roi_out) {
-      int32_t* o = a.view_roi_out + 4 * (size_t)b;
-      o[0] = vx0; o[1] = vy0; o[2] = vx1; o[3] = vy1;
-    }
+    c.vx0 = (int)rintf(add(sub(cx, hs), tx)); c.vy0 = (int)rintf(add(sub(cy, hs), ty));
+    c.vx1 = (int)rintf(add(add(cx, hs), tx)); c.vy1 = (int)rintf(add(add(cy, hs), ty));
     // geometric.py:159-178: tr = (denorm @ rot @ norm) @ range_remap(view -> [0,out])
-    Aff tr_roi = aff_range_remap((float)vx0, (float)vy0, (float)vx1, (float)vy1, 0.f, 0.f, (float)ow, (float)oh);
+    Aff tr_roi = aff_range_remap((float)c.vx0, (float)c.vy0, (float)c.vx1, (float)c.vy1, 0.f, 0.f, (float)ow, (float)oh);
     Aff nrm = aff_range_remap(0.f, 0.f, (float)ow, (float)oh, -1.f, -1.f, 1.f, 1.f);
     Aff den = aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, (float)ow, (float)oh);
-    if (!a.cos_sin) cos_sin_rn(angle, cs, sn);
+    if (!a.cos_sin) cos_sin_rn(c.angle, cs, sn);
     Aff rot = Aff{cs, -sn, 0.f, sn, cs, 0.f};
-    t1 = aff_compose(aff_compose(aff_compose(den, rot), nrm), tr_roi);
-
-    P.x0 = vx0;
-    P.y0 = vy0;
-    if (angle != 0.f) {
+    c.t1 = aff_compose(aff_compose(aff_compose(den, rot), nrm), tr_roi);
+    if (c.angle != 0.f) {
       // affine_transform_image_cv2, image_geometric_cv2.py:85-135
-      P.src_mode = SRC_WARP;
-      double sf = (double)aff_scales(t1);
-      Aff M;
+      c.src_mode = SRC_WARP;
+      double sf = (double)aff_scales(c.t1);
       if (sf > 1.0) {
-        M = aff_compose(t1, Aff{1.f, 0.f, 0.5f, 0.f, 1.f, 0.5f});
-        P.cw = ow;
-        P.ch = oh;
+        c.cw = ow;
+        c.ch = oh;
       } else {
-        P.cw = rint_d2i((double)ow / sf);  // Python round(): half to even on doubles
-        P.ch = rint_d2i((double)oh / sf);
-        float sc = (float)((double)P.ch / (double)oh);
-        M = aff_compose(Aff{sc, 0.f, 0.f, 0.f, sc, 0.f}, t1);
+        c.cw = rint_d2i((double)ow / sf);  // Python round(): half to even on doubles
+        c.ch = rint_d2i((double)oh / sf);
       }
-      // cv2.warpAffine: invert in double (no FMA), oracle/cv2_model.py:invert_affine_f64
-      double m0 = M.a00, m1 = M.a01, m2 = M.a02, m3 = M.a10, m4 = M.a11, m5 = M.a12;
-      double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
-      D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
-      double A11 = __dmul_rn(m4, D), A22 = __dmul_rn(m0, D);
-      m0 = A11;
-      m1 = __dmul_rn(m1, -D);
-      m3 = __dmul_rn(m3, -D);
-      m4 = A22;
-      double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
-      double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
-      P.mi[0] = m0; P.mi[1] = m1; P.mi[2] = b1; P.mi[3] = m3; P.mi[4] = m4; P.mi[5] = b2;
     } else {
-      P.src_mode = SRC_CROP;
-      P.cw = vx1 - vx0;
-      P.ch = vy1 - vy0;
+      c.src_mode = SRC_CROP;
+      c.cw = c.vx1 - c.vx0;
+      c.ch = c.vy1 - c.vy0;
     }
-    W = ow;
-    H = oh;
+    c.W = ow;
+    c.H = oh;
   } else {
-    // no geometric stage: the source already is the crop
-    P.src_mode = SRC_PLAIN;
-    P.x0 = 0;
-    P.y0 = 0;
-    P.cw = P.sw;
-    P.ch = P.sh;
+    c.src_mode = SRC_PLAIN;  // no geometric stage: the source already is the crop
+    c.cw = c.s.width;
+    c.ch = c.s.height;
   }
-  P.t1 = aff_derive(t1);
-  if (a.tr_out && focus) {
-    float* o = a.tr_out + 6 * (size_t)b;
-    o[0] = t1.a00; o[1] = t1.a01; o[2] = t1.a02; o[3] = t1.a10; o[4] = t1.a11; o[5] = t1.a12;
-  }
-  if (a.backtransform_out && focus) {
-    Aff iv = aff_inv(t1);
-    float* o = a.backtransform_out + 6 * (size_t)b;
-    o[0] = iv.a00; o[1] = iv.a01; o[2] = iv.a02; o[3] = iv.a10; o[4] = iv.a11; o[5] = iv.a12;
-  }
+  return c;
+}
 
-  // resize decision, image_geometric_cv2.py:65-82 + cv::resize dispatch
-  if (P.cw <= 0 || P.ch <= 0) {
+// branch 0: plain fields + the dst->src map of cv2.warpAffine
+__device__ void plan_basic_and_warp(const B200AugFusedArgs& a, const PlanCore& c, Plan& P) {
+  const int ow = a.out_w, oh = a.out_h;
+  P.kx = 0;
+  P.src = c.s.ptr;
+  P.sw = c.s.width;
+  P.sh = c.s.height;
+  P.pitch = c.s.pitch;
+  P.do_flip = c.do_flip;
+  P.rot_dir = c.rot_dir;
+  P.src_mode = c.src_mode;
+  P.cw = c.cw;
+  P.ch = c.ch;
+  P.x0 = (c.src_mode == SRC_PLAIN) ? 0 : c.vx0;
+  P.y0 = (c.src_mode == SRC_PLAIN) ? 0 : c.vy0;
+  if (c.src_mode == SRC_WARP) {
+    Aff M;
+    if (c.cw == ow && c.ch == oh && (double)aff_scales(c.t1) > 1.0) {
+      M = aff_compose(c.t1, Aff{1.f, 0.f, 0.5f, 0.f, 1.f, 0.5f});
+    } else {
+      float sc = (float)((double)c.ch / (double)oh);
+      M = aff_compose(Aff{sc, 0.f, 0.f, 0.f, sc, 0.f}, c.t1);
+    }
+    // cv2.warpAffine: invert in double (no FMA), oracle/cv2_model.py:invert_affine_f64
+    double m0 = M.a00, m1 = M.a01, m2 = M.a02, m3 = M.a10, m4 = M.a11, m5 = M.a12;
+    double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
+    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+    double A11 = __dmul_rn(m4, D), A22 = __dmul_rn(m0, D);
+    m0 = A11;
+    m1 = __dmul_rn(m1, -D);
+    m3 = __dmul_rn(m3, -D);
+    m4 = A22;
+    double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
+    double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
+    P.mi[0] = m0; P.mi[1] = m1; P.mi[2] = b1; P.mi[3] = m3; P.mi[4] = m4; P.mi[5] = b2;
+  }
+}
+
+// branch 1: resize decision, image_geometric_cv2.py:65-82 + cv::resize dispatch
+__device__ void plan_resize(const B200AugFusedArgs& a, const PlanCore& c, Plan& P) {
+  const int ow = a.out_w, oh = a.out_h;
+  P.status = B200AUG_S_OK;
+  P.fin = 0;
+  if (c.cw <= 0 || c.ch <= 0) {
     P.status = B200AUG_S_EMPTY_BOX;
     P.rs_mode = RS_COPY;
-  } else if (P.cw == ow && P.ch == oh) {
+  } else if (c.cw == ow && c.ch == oh) {
     P.rs_mode = RS_COPY;
   } else {
-    double scale_factor = 0.5 * ((double)ow / (double)P.cw + (double)oh / (double)P.ch);
-    P.scale_x = 1.0 / ((double)ow / (double)P.cw);
-    P.scale_y = 1.0 / ((double)oh / (double)P.ch);
+    double scale_factor = 0.5 * ((double)ow / (double)c.cw + (double)oh / (double)c.ch);
+    P.scale_x = 1.0 / ((double)ow / (double)c.cw);
+    P.scale_y = 1.0 / ((double)oh / (double)c.ch);
     if (scale_factor < 1.0) {
       if (P.scale_x >= 1.0 && P.scale_y >= 1.0) {
         P.iscale_x = rint_d2i(P.scale_x);
@@ -302,55 +327,67 @@ __device__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, const floa
       P.rs_mode = RS_LINEAR;
     }
   }
+}
 
-  // horizontal_flip_and_rot_90 label transform, geometric.py:242-252
-  P.has_t2 = (P.do_flip || P.rot_dir != 0);
+// horizontal_flip_and_rot_90 label transform, geometric.py:242-252
+__device__ Aff fliprot_transform(const PlanCore& c) {
   Aff t2 = aff_identity();
-  if (P.has_t2) {
-    float w = (float)W, h = (float)H;
-    if (P.rot_dir != 0) {
-      t2 = aff_compose(t2, aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, w, h));
-      // float32(cos), float32(sin) of float32(+-pi/2), as torch evaluates them (affine2d.py:46-47)
-      const float c90 = -0x1.777a5cp-25f, s90 = (P.rot_dir > 0) ? 1.f : -1.f;
-      t2 = aff_compose(t2, Aff{c90, -s90, 0.f, s90, c90, 0.f});
-      t2 = aff_compose(t2, aff_range_remap(0.f, 0.f, w, h, -1.f, -1.f, 1.f, 1.f));
-    }
-    if (P.do_flip) t2 = aff_compose(t2, aff_range_remap(0.f, 0.f, w, h, w, 0.f, 0.f, h));
-    P.t2 = aff_derive(t2);
+  float w = (float)c.W, h = (float)c.H;
+  if (c.rot_dir != 0) {
+    t2 = aff_compose(t2, aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, w, h));
+    // float32(cos), float32(sin) of float32(+-pi/2), as torch evaluates them (affine2d.py:46-47)
+    const float c90 = -0x1.777a5cp-25f, s90 = (c.rot_dir > 0) ? 1.f : -1.f;
+    t2 = aff_compose(t2, Aff{c90, -s90, 0.f, s90, c90, 0.f});
+    t2 = aff_compose(t2, aff_range_remap(0.f, 0.f, w, h, -1.f, -1.f, 1.f, 1.f));
   }
-  // normalize_batch label transform, normalization.py:36-40
-  P.t3 = aff_derive(aff_range_remap(0.f, 0.f, (float)W, (float)H, -1.f, -1.f, 1.f, 1.f));
-  int nflip = (P.t1.det < 0.f) + (P.has_t2 && P.t2.det < 0.f);
-  P.flip_parity = nflip & 1;
+  if (c.do_flip) t2 = aff_compose(t2, aff_range_remap(0.f, 0.f, w, h, w, 0.f, 0.f, h));
+  return t2;
+}
 
-  // photometric parameters of this sample
+// normalize_batch label transform, normalization.py:36-40
+__device__ __forceinline__ Aff normalize_transform(const PlanCore& c) {
+  return aff_range_remap(0.f, 0.f, (float)c.W, (float)c.H, -1.f, -1.f, 1.f, 1.f);
+}
+
+// branch 5: photometric parameters of this sample
+__device__ void plan_photo(const B200AugFusedArgs& a, int b, Plan& P) {
   P.n_ops = 0;
   P.blur_pos = -1;
   P.eq_pos = -1;
   P.eq_step0 = 0;
   P.any_noise = 0;
-  if (photo) {
-    const B200AugPhotoParams& pp = a.photo;
-    for (int k = 0; k < pp.n_order; ++k) {
-      const int op = pp.order[k];
-      bool on = false;
+  if (!(a.flags & B200AUG_F_PHOTOMETRIC)) return;
+  const B200AugPhotoParams& pp = a.photo;
+  uint8_t op_on[B200AUG_NUM_OPS] = {0, 0, 0, 0, 0, 0}, noise_on[B200AUG_NUM_NOISE] = {0, 0, 0, 0};
+  if (pp.apply)
 #pragma unroll
-      for (int q = 0; q < B200AUG_NUM_OPS; ++q) on = on || (q == op && op_on[q]);
-      if (on) {
-        if (op == B200AUG_OP_BLUR) P.blur_pos = P.n_ops;
-        if (op == B200AUG_OP_EQUALIZE) P.eq_pos = P.n_ops;
-        P.ops[P.n_ops++] = op;
-      }
-    }
-    P.bits = bits;
-    P.gamma = gamma;
-    P.contrast = contrast;
-    P.brightness_shift = sub(brightness, 1.f);
+    for (int k = 0; k < B200AUG_NUM_OPS; ++k) op_on[k] = pp.apply[(size_t)b * B200AUG_NUM_OPS + k];
+  if (pp.noise_apply)
 #pragma unroll
-    for (int q = 0; q < B200AUG_NUM_NOISE; ++q) {
-      P.noise_on[q] = noise_on[q];
-      P.any_noise |= noise_on[q];
+    for (int k = 0; k < B200AUG_NUM_NOISE; ++k) noise_on[k] = pp.noise_apply[(size_t)b * B200AUG_NUM_NOISE + k];
+  const int bits = pp.bits ? pp.bits[b] : 8;
+  const float gamma = pp.gamma ? pp.gamma[b] : 1.f;
+  const float contrast = pp.contrast ? pp.contrast[b] : 1.f;
+  const float brightness = pp.brightness ? pp.brightness[b] : 1.f;
+  for (int k = 0; k < pp.n_order; ++k) {
+    const int op = pp.order[k];
+    bool on = false;
+#pragma unroll
+    for (int q = 0; q < B200AUG_NUM_OPS; ++q) on = on || (q == op && op_on[q]);
+    if (on) {
+      if (op == B200AUG_OP_BLUR) P.blur_pos = P.n_ops;
+      if (op == B200AUG_OP_EQUALIZE) P.eq_pos = P.n_ops;
+      P.ops[P.n_ops++] = op;
     }
+  }
+  P.bits = bits;
+  P.gamma = gamma;
+  P.contrast = contrast;
+  P.brightness_shift = sub(brightness, 1.f);
+#pragma unroll
+  for (int q = 0; q < B200AUG_NUM_NOISE; ++q) {
+    P.noise_on[q] = noise_on[q];
+    P.any_noise |= noise_on[q];
   }
 }
 
@@ -379,6 +416,8 @@ __device__ void run_item_chain(const Plan& P, uint32_t flags, int category, floa
 
 // `staged`: the transformable fields of this sample, packed in field order in shared memory (or NULL)
 __device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b, const float* staged) {
+  // an odd number of mirroring transforms permutes the left/right landmarks
+  const bool flip_parity = (((a.flags & B200AUG_F_FOCUS) && P.t1.det < 0.f) + (P.has_t2 && P.t2.det < 0.f)) & 1;
   int off = 0;
   for (int f = 0; f < a.n_fields; ++f) {
     const B200AugField& F = a.fields[f];
@@ -399,7 +438,7 @@ __device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b
     if (is_roi_from_lm) continue;  // written by warp 0 in the prologue
     for (int i = threadIdx.x; i < cnt; i += NTHREADS) {
       int si = i;
-      if (F.category == B200AUG_CAT_POINTS && cnt == 68 && P.flip_parity) si = flip_map68(i);
+      if (F.category == B200AUG_CAT_POINTS && cnt == 68 && flip_parity) si = flip_map68(i);
       float v[4];
       for (int k = 0; k < dim; ++k) v[k] = in[si * dim + k];
       run_item_chain(P, a.flags, F.category, v, dim);
@@ -624,7 +663,7 @@ constexpr int WT_ROWS = 39;             // tallest bounding box of a 32 x 16 til
 // straight from global memory would touch ~16 cache lines per warp instruction.  Tiles whose bounding box leaves the
 // frame (BORDER_CONSTANT zeros) or is too large (a down-scaling canvas never is) take the predicated global path.
 __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ dtab, uint8_t* stage, int stage_bytes,
-                                       uint8_t* __restrict__ scratch, int spitch, int warp, int lane) {
+                                       uint8_t* __restrict__ scratch, int spitch, int warp, int lane, int cr, int cl) {
   const uint8_t* __restrict__ src = P.src;
   const int pitch = P.pitch, sw = P.sw, sh = P.sh, cw = P.cw, ch = P.ch;
   const double m1 = P.mi[1], m2 = P.mi[2], m4 = P.mi[4], m5 = P.mi[5];
@@ -635,7 +674,7 @@ __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ d
     X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
     Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
   };
-  for (int t = warp; t < tiles_x * tiles_y; t += NWARPS) {
+  for (int t = cr * NWARPS + warp; t < tiles_x * tiles_y; t += cl * NWARPS) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x_lo = tx * WT_W, y_lo = ty * WT_H;
     const int tw = min(WT_W, cw - x_lo), th = min(WT_H, ch - y_lo);
@@ -766,8 +805,9 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 // supersets of the row segment) in flight, each completing on its slot's mbarrier.  Rows on the frame border are
 // staged synchronously (zero padded), rows outside the frame are zero, warp rows are computed into the staging row.
 template <int K, bool is_warp>
-__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int warp, int lane) {
-  const int dy_begin = (warp * oh) / NWARPS, dy_end = ((warp + 1) * oh) / NWARPS;
+__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int warp, int lane, int cr, int cl) {
+  const int rows_lo = (cr * oh) / cl, rows_n = ((cr + 1) * oh) / cl - rows_lo;  // this CTA's band of output rows
+  const int dy_begin = rows_lo + (warp * rows_n) / NWARPS, dy_end = rows_lo + ((warp + 1) * rows_n) / NWARPS;
   if (dy_begin >= dy_end) return;
   // everything lives in this CTA's dynamic shared memory; deriving the pointers here keeps the address space known
   // (a generic pointer passed into a non-inlined function turns every table read into a generic load)
@@ -784,6 +824,9 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   uint8_t* const rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
   const int2* const dtab = reinterpret_cast<const int2*>(smem + L.off_dtab);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
+  uint32_t tile_c[MAX_CLUSTER];  // the tile of every CTA of the cluster (distributed shared memory)
+#pragma unroll
+  for (int q = 0; q < MAX_CLUSTER; ++q) tile_c[q] = map_to_rank(smem_u32(tile), min(q, cl - 1));
   // plan fields used per row live in registers (the tile stores would otherwise force reloads from shared memory)
   const uint8_t* const src = P.src;
   const int pitch = P.pitch, x0 = P.x0, y0 = P.y0, sw = P.sw, sh = P.sh, cw = P.cw;
@@ -899,7 +942,15 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
           if (fin == 0) q = cvt_rni_sat_u8(acc[j]);
           else if (fin == 1) q = (uint32_t)(((int)acc[j] + 2) >> 2);
           else q = cvt_rni_sat_u8(__fmul_rn(acc[j], inv_area));
-          if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)q;
+          if (tcol[j] >= 0) {
+            if (cl == 1) {
+              tile[tcol[j] + trow] = (uint8_t)q;
+            } else {
+#pragma unroll
+              for (int c = 0; c < MAX_CLUSTER; ++c)
+                if (c < cl) st_cluster_u8(tile_c[c] + (uint32_t)(tcol[j] + trow), q);
+            }
+          }
         }
         ++dy;
         k = 0;
@@ -988,7 +1039,10 @@ __device__ float blurred_value(const uint8_t* tile, const float* lut, int ow, in
 __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap) {
   const B200AugFusedArgs& a = K.a;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int b = blockIdx.x;
+  uint32_t cr_u, cl_u;
+  cluster_info(cr_u, cl_u);
+  const int cr = (int)cr_u, cl = (int)cl_u;  // rank in / size of the cluster that shares this sample
+  const int b = blockIdx.x / cl;
   const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SmemLayout L = smem_layout(ow, oh, cap);
@@ -1009,11 +1063,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
   float* lab = reinterpret_cast<float*>(smem + L.off_lab);
 
-  trace_mark(a, b, 0);
+  trace_mark(a, 0);
   if (a.trace_out && tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    a.trace_out[(size_t)b * 8 + 5] = smid;
+    a.trace_out[(size_t)blockIdx.x * 8 + 5] = smid;
   }
   if (lane == 0) {
     for (int s = 0; s < RING_MAX; ++s) mbar_init(&bars[s], 1);
@@ -1037,8 +1091,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       off += n;
     }
   }
-  // ---- prologue: warp 0 builds the plan ------------------------------------------------------------------
-  if (warp == 0) {
+  // ---- prologue: the plan, one branch per warp (see plan_core) --------------------------------------------
+  {
     float box[4] = {0.f, 0.f, 0.f, 0.f};
     const bool lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && a.landmark_field >= 0;
     const bool half = a.flags & B200AUG_F_HALF_PIXEL;
@@ -1049,26 +1103,66 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       const float* r = a.fields[a.roi_field].in + 4 * (size_t)b;
       box[0] = r[0]; box[1] = r[1]; box[2] = r[2]; box[3] = r[3];
     }
-    if (lane == 0) build_plan(a, b, P, box);
-    __syncwarp();
-    if (lm && a.roi_field >= 0 && a.fields[a.roi_field].out) {
-      // landmarks mode: the roi label is regenerated from the transformed landmarks after the crop (pipelines.py:347-351)
-      const B200AugField& F = a.fields[a.landmark_field];
-      float nb[4];
-      landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, half, (a.flags & B200AUG_F_FOCUS) ? &P.t1 : nullptr, nb);
-      if (lane == 0) {
-        if ((a.flags & B200AUG_F_FLIPROT) && P.has_t2) tf_roi(P.t2, nb);
-        if (a.flags & B200AUG_F_NORMALIZE) tf_roi(P.t3, nb);
-        float* o = a.fields[a.roi_field].out + 4 * (size_t)b;
-        o[0] = nb[0]; o[1] = nb[1]; o[2] = nb[2]; o[3] = nb[3];
-      }
+    const PlanCore c = plan_core(a, b, box);
+    const bool focus = a.flags & B200AUG_F_FOCUS;
+    switch (warp) {
+      case 0:
+        if (lane == 0) plan_basic_and_warp(a, c, P);
+        break;
+      case 1:
+        if (lane == 0) plan_resize(a, c, P);
+        break;
+      case 2: {
+        const AffDerived d1 = aff_derive(c.t1);
+        if (lane == 0) {
+          P.t1 = d1;
+          if (a.view_roi_out && focus) {
+            int32_t* o = a.view_roi_out + 4 * (size_t)b;
+            o[0] = c.vx0; o[1] = c.vy0; o[2] = c.vx1; o[3] = c.vy1;
+          }
+          if (a.tr_out && focus) {
+            float* o = a.tr_out + 6 * (size_t)b;
+            o[0] = c.t1.a00; o[1] = c.t1.a01; o[2] = c.t1.a02; o[3] = c.t1.a10; o[4] = c.t1.a11; o[5] = c.t1.a12;
+          }
+          if (a.backtransform_out && focus) {
+            Aff iv = aff_inv(c.t1);
+            float* o = a.backtransform_out + 6 * (size_t)b;
+            o[0] = iv.a00; o[1] = iv.a01; o[2] = iv.a02; o[3] = iv.a10; o[4] = iv.a11; o[5] = iv.a12;
+          }
+        }
+        if (lm && a.roi_field >= 0 && a.fields[a.roi_field].out) {
+          // landmarks mode: the roi label is regenerated from the transformed landmarks after the crop (pipelines.py:347-351)
+          const B200AugField& F = a.fields[a.landmark_field];
+          float nb[4];
+          landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, half, focus ? &d1 : nullptr, nb);
+          if (lane == 0 && cr == 0) {
+            if ((a.flags & B200AUG_F_FLIPROT) && (c.do_flip || c.rot_dir != 0)) tf_roi(aff_derive(fliprot_transform(c)), nb);
+            if (a.flags & B200AUG_F_NORMALIZE) tf_roi(aff_derive(normalize_transform(c)), nb);
+            float* o = a.fields[a.roi_field].out + 4 * (size_t)b;
+            o[0] = nb[0]; o[1] = nb[1]; o[2] = nb[2]; o[3] = nb[3];
+          }
+        }
+      } break;
+      case 3:
+        if (lane == 0) {
+          P.has_t2 = (c.do_flip || c.rot_dir != 0);
+          if (P.has_t2) P.t2 = aff_derive(fliprot_transform(c));
+        }
+        break;
+      case 4:
+        if (lane == 0) P.t3 = aff_derive(normalize_transform(c));
+        break;
+      case 5:
+        if (lane == 0) plan_photo(a, b, P);
+        break;
+      default: break;
     }
   }
   __syncthreads();
 
-  trace_mark(a, b, 1);
+  trace_mark(a, 1);
   if (tid == 0 && a.status_out) a.status_out[b] = P.status;
-  transform_labels(a, P, b, lab_staged ? lab : nullptr);
+  if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
 
   const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
   if (!want_image) return;
@@ -1108,16 +1202,17 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     hist8[tid] = 0;
     binhist[tid] = 0;
   }
-  __syncthreads();
+  trace_mark(a, 7);
+  cluster_sync(cl);  // (also: every CTA of the cluster is running before any distributed-shared-memory access)
 
-  trace_mark(a, b, 2);
+  trace_mark(a, 2);
   // ---- rotated samples, stage 1: warpAffine into this sample's scratch canvas; stage 2 is then a plain crop of it ----
   if (use_dtab && a.workspace && P.status == B200AUG_S_OK) {
     const int spitch = (P.cw + 16 + 15) & ~15;  // 16-byte aligned rows with room for the bulk copies' over-read
     if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
       uint8_t* scratch = a.workspace + (size_t)b * a.workspace_stride;
-      warp_canvas_to_scratch(P, dtab, rowbuf, cap + ROWBUF_SLACK, scratch, spitch, warp, lane);
-      __syncthreads();
+      warp_canvas_to_scratch(P, dtab, rowbuf, cap + ROWBUF_SLACK, scratch, spitch, warp, lane, cr, cl);
+      cluster_sync(cl);  // the tiles were produced by all CTAs of the cluster
       if (tid == 0) {
         P.src = scratch;
         P.pitch = spitch;
@@ -1130,7 +1225,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       __syncthreads();
     }
   }
-  trace_mark(a, b, 6);
+  trace_mark(a, 6);
   // ---- resample into the uint8 tile -----------------------------------------------------------------------
   const TileMap tm = make_tile_map(P, ow, oh);
   bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) &&
@@ -1145,7 +1240,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   if (fast) {
     const int kx = P.kx;
 #define B200AUG_BAND(KK)                                                                                   \
-  (P.src_mode == SRC_WARP ? area_band<KK, true>(tm, cap, ow, oh, warp, lane) : area_band<KK, false>(tm, cap, ow, oh, warp, lane))
+  (P.src_mode == SRC_WARP ? area_band<KK, true>(tm, cap, ow, oh, warp, lane, cr, cl)                      \
+                          : area_band<KK, false>(tm, cap, ow, oh, warp, lane, cr, cl))
     if (kx <= 3) B200AUG_BAND(3);
     else if (kx == 4) B200AUG_BAND(4);
     else if (kx == 5) B200AUG_BAND(5);
@@ -1153,21 +1249,27 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
 #undef B200AUG_BAND
   } else if (P.status == B200AUG_S_OK) {
     // per-pixel path: integer-factor area, linear up-scaling, plain copy, very wide taps / canvases
-    for (int p = tid; p < npix; p += NTHREADS) {
+    uint32_t tile_c[MAX_CLUSTER];
+#pragma unroll
+    for (int q = 0; q < MAX_CLUSTER; ++q) tile_c[q] = map_to_rank(smem_u32(tile), min(q, cl - 1));
+    for (int p = (cr * npix) / cl + tid; p < ((cr + 1) * npix) / cl; p += NTHREADS) {
       const int dy = p / ow, dx = p - dy * ow;
-      tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
+      const uint32_t v = scalar_out_px(P, T, ow, dx, dy);
+#pragma unroll
+      for (int c = 0; c < MAX_CLUSTER; ++c)
+        if (c < cl) st_cluster_u8(tile_c[c] + (uint32_t)(tm.o + dy * tm.sa + dx * tm.sb), v);
     }
   } else {
     for (int p = tid; p < npix; p += NTHREADS) tile[p] = 0;
   }
-  __syncthreads();
-  trace_mark(a, b, 3);
+  cluster_sync(cl);  // every CTA's tile now holds the whole crop; no distributed-shared-memory access after this point
+  trace_mark(a, 3);
 
   // ---- uint8 output (geometric stages only) --------------------------------------------------------------
   if (!(a.flags & B200AUG_F_NORMALIZE)) {
     uint8_t* out = a.image_u8_out + (size_t)b * npix;
-    for (int p = tid; p < npix; p += NTHREADS) out[p] = tile[p];
-    trace_mark(a, b, 4);
+    for (int p = (cr * npix) / cl + tid; p < ((cr + 1) * npix) / cl; p += NTHREADS) out[p] = tile[p];
+    trace_mark(a, 4);
     return;
   }
 
@@ -1252,21 +1354,22 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   // ---- output pass ----------------------------------------------------------------------------------------
   float* out = a.image_f32_out + (size_t)b * npix;
   const int Q = (npix + 3) >> 2;
+  const int g_lo = (cr * Q) / cl, g_hi = ((cr + 1) * Q) / cl;  // this CTA's share of the output
   if (folded) {
-    for (int g = tid; g < Q; g += NTHREADS) {
+    for (int g = g_lo + tid; g < g_hi; g += NTHREADS) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int p = g + i * Q;
         if (p < npix) out[p] = lut[tile[p]];
       }
     }
-    trace_mark(a, b, 4);
+    trace_mark(a, 4);
     return;
   }
   const uint64_t sid = a.photo.sample_offset + (uint64_t)b;
   const uint2 key = make_uint2((uint32_t)a.photo.seed, (uint32_t)(a.photo.seed >> 32));
   const bool blur = P.blur_pos >= 0;
-  for (int g = tid; g < Q; g += NTHREADS) {
+  for (int g = g_lo + tid; g < g_hi; g += NTHREADS) {
     float x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1302,7 +1405,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       }
     }
   }
-  trace_mark(a, b, 4);
+  trace_mark(a, 4);
 }
 
 // ------------------------------------------------------------------------------------------------ apply_affine2d
@@ -1423,8 +1526,22 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
   KArgs K;
   K.a = a;
-  fused_augment_kernel<<<a.batch, NTHREADS, smem, (cudaStream_t)stream>>>(K, cap);
-  e = cudaGetLastError();
+  int cl = a.cluster_size > 0 ? a.cluster_size : DEFAULT_CLUSTER;
+  if (cl != 1 && cl != 2 && cl != 4) return B200AUG_E_INVALID_ARG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)a.batch * cl);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, fused_augment_kernel, K, cap);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
   return B200AUG_OK;
 }

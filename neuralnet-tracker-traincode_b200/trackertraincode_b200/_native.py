@@ -38,7 +38,7 @@ class FusedArgs(C.Structure):
                 ("src_table", C.c_void_p), ("src_uniform", Src), ("src_stride", C.c_int64),
                 ("scales", C.c_void_p), ("angles", C.c_void_p), ("cos_sin", C.c_void_p), ("translations", C.c_void_p),
                 ("beyond_border_shift", C.c_float), ("do_flip", C.c_void_p), ("rot_dir", C.c_void_p),
-                ("n_fields", C.c_int32), ("roi_field", C.c_int32), ("landmark_field", C.c_int32), ("reserved", C.c_int32),
+                ("n_fields", C.c_int32), ("roi_field", C.c_int32), ("landmark_field", C.c_int32), ("cluster_size", C.c_int32),
                 ("fields", Field * MAX_FIELDS),
                 ("view_roi_out", C.c_void_p), ("tr_out", C.c_void_p), ("backtransform_out", C.c_void_p),
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),

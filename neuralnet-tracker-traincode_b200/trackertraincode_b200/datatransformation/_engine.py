@@ -186,7 +186,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   photo: Optional[PhotoParams] = None, roi_variable: str = "roi", landmark_variable: str = "pt3d_68",
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
-                  want_trace: bool = False, use_workspace: bool = True) -> PreparedCall:
+                  want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -202,6 +202,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     args.rowbuf_capacity = rowbuf_capacity
     args.beyond_border_shift = beyond_border_shift
     args.roi_field = args.landmark_field = -1
+    args.cluster_size = cluster_size
     keep: List[Any] = []
     out_data: Dict[str, Any] = {}
 
@@ -323,7 +324,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         args.status_out = status.data_ptr()
     trace = None
     if want_trace:  # per-CTA timeline (profiling aid, see include/b200aug.h: trace_out)
-        trace = torch.zeros((B, 8), dtype=torch.int64, device=device)
+        trace = torch.zeros((B * (cluster_size or 2), 8), dtype=torch.int64, device=device)
         args.trace_out = trace.data_ptr()
 
     # ---- assemble the result (tensors are written when the call is launched)

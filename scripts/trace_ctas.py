@@ -26,22 +26,26 @@ an = torch.from_numpy(gp.angles)
 geo = E.GeoParams(torch.from_numpy(gp.scales), an, torch.from_numpy(gp.translations), E.host_cos_sin(an))
 flags = N.F_HALF_PIXEL | N.F_FOCUS | N.F_FLIPROT | N.F_NORMALIZE | N.F_PHOTOMETRIC | N.F_WHITEN
 call = E.prepare_fused(b, flags=flags, out_size=bench.OUT, geo=geo, do_flip=torch.from_numpy(gp.do_flip.astype(np.uint8)),
-                       rot_dir=torch.from_numpy(gp.rot_dir), photo=photo, want_status=True, want_trace=True, want_view_roi=True)
+                       rot_dir=torch.from_numpy(gp.rot_dir), photo=photo, want_status=True, want_trace=True, want_view_roi=True,
+                       cluster_size=int(os.environ.get("B200AUG_CLUSTER", "0")))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(5):
     flush.zero_()
     call.launch()
 torch.cuda.synchronize()
 t = call.result.trace.cpu().numpy().astype(np.int64)
+CL = int(os.environ.get("B200AUG_CLUSTER", "0")) or 2
+t = t[: bench.BATCH * CL]
 t0 = t[:, 0].min()
 start, plan, tabs, res, end, smid = (t[:, i] - (t0 if i < 5 else 0) for i in range(6))
 print(f"kernel span {(end.max()) / 1e3:.1f} us; CTA duration us: mean {np.mean(end - start) / 1e3:.1f} median {np.median(end - start) / 1e3:.1f} "
       f"p95 {np.percentile(end - start, 95) / 1e3:.1f} max {(end - start).max() / 1e3:.1f}")
-rot = gp.angles != 0
-blur = pp.apply[:, 5] & (5 in list(pp.order))
-eq = pp.apply[:, 0] & (0 in list(pp.order))
-noise = pp.noise_apply.any(1)
-ph = {"plan": plan - start, "labels+tables": tabs - plan, "resample": res - tabs, "photo+output": end - res, "total": end - start}
+rot = np.repeat(gp.angles != 0, CL)
+blur = np.repeat(pp.apply[:, 5] & (5 in list(pp.order)), CL)
+eq = np.repeat(pp.apply[:, 0] & (0 in list(pp.order)), CL)
+noise = np.repeat(pp.noise_apply.any(1), CL)
+warp_stage = t[:, 6] - t0 - tabs
+ph = {"plan": plan - start, "lab+tab": t[:, 7] - t0 - plan, "csync": tabs - (t[:, 7] - t0), "warp": warp_stage, "resample": res - tabs, "photo+output": end - res, "total": end - start}
 for name, m in (("all", np.ones_like(rot)), ("unrotated", ~rot), ("rotated", rot), ("blur", blur), ("equalize", eq), ("noise", noise),
                 ("plain(no rot/photo)", ~rot & ~blur & ~eq & ~noise)):
     if m.sum():
@@ -50,11 +54,12 @@ print("start-time histogram (us):", np.histogram(start / 1e3, bins=10)[0].tolist
 busy = np.zeros(int(smid.max()) + 1)
 for s, a, e in zip(smid, start, end):
     busy[s] = max(busy[s], e)
+sys.stdout.flush()
 print(f"per-SM last-CTA end (us): min {busy.min() / 1e3:.1f} median {np.median(busy) / 1e3:.1f} max {busy.max() / 1e3:.1f}; SMs used {len(np.unique(smid))}")
-vr = call.result.view_roi.cpu().numpy()
+vr = np.repeat(call.result.view_roi.cpu().numpy(), CL, axis=0)
 dur = end - start
 for i in np.argsort(-dur)[:8]:
-    print(f"slow sample {i}: total {dur[i] / 1e3:.1f} us resample {(res - tabs)[i] / 1e3:.1f} view_roi {vr[i].tolist()} size {(vr[i, 2] - vr[i, 0], vr[i, 3] - vr[i, 1])} "
+    print(f"slow cta {i} (sample {i // CL}): total {dur[i] / 1e3:.1f} us resample {(res - tabs)[i] / 1e3:.1f} view_roi {vr[i].tolist()} size {(vr[i, 2] - vr[i, 0], vr[i, 3] - vr[i, 1])} "
           f"rot {bool(rot[i])} blur {bool(blur[i])} eq {bool(eq[i])} noise {bool(noise[i])} sm {smid[i]} start {start[i] / 1e3:.1f}")
 if len(sys.argv) > 1:
     np.savez(sys.argv[1], trace=t, rot=rot, blur=blur, eq=eq, noise=noise)
