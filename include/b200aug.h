@@ -147,6 +147,10 @@ typedef struct B200AugFusedArgs {
   int32_t* status_out;          /* [B] B200AUG_S_* */
   uint64_t* trace_out;          /* [B*cluster_size,8] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / tables
                                    built / resample done / end, then %smid, warp stage done, 0 */
+  /* optional launch order: order[i] = sample processed by the i-th cluster of the grid (a permutation of 0..B-1).  The
+   * CTAs are dispatched in grid order, so listing the expensive samples (rotated, blurred, noisy) first lets the cheap
+   * ones fill the tail.  NULL = identity. */
+  const int32_t* order;
   /* optional scratch for rotated samples: B regions of workspace_stride bytes (see b200aug_workspace_stride()).  The
    * two-stage rotated path (warpAffine canvas, then INTER_AREA; image_geometric_cv2.py:121-134) keeps its canvas here,
    * i.e. in L2.  Without it (NULL) or when a canvas does not fit, canvas rows are produced one at a time instead. */

@@ -92,7 +92,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ow, int oh, int cap) {
   L.off_dtab = o;
   o += (size_t)DT_CAP * sizeof(int2);
   L.off_bars = o;
-  o += (size_t)NWARPS * RING_MAX * sizeof(uint64_t);
+  o += (size_t)(NWARPS * RING_MAX + 2) * sizeof(uint64_t);  // ring barriers + the cluster exchange barrier
   L.off_lab = o;
   o += (size_t)LAB_CAP * sizeof(float);
   L.total = o;
@@ -130,6 +130,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar32, uint32_t parity) {
         : "r"(bar32), "r"(parity)
         : "memory");
     if (spins > (1u << 26)) __trap();
+  }
+}
+
+// cp.async.wait_group takes an immediate: wait until at most `n` (0..7) of this thread's commit groups are pending
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
   }
 }
 
@@ -824,9 +838,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   uint8_t* const rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
   const int2* const dtab = reinterpret_cast<const int2*>(smem + L.off_dtab);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
-  uint32_t tile_c[MAX_CLUSTER];  // the tile of every CTA of the cluster (distributed shared memory)
-#pragma unroll
-  for (int q = 0; q < MAX_CLUSTER; ++q) tile_c[q] = map_to_rank(smem_u32(tile), min(q, cl - 1));
+
   // plan fields used per row live in registers (the tile stores would otherwise force reloads from shared memory)
   const uint8_t* const src = P.src;
   const int pitch = P.pitch, x0 = P.x0, y0 = P.y0, sw = P.sw, sh = P.sh, cw = P.cw;
@@ -835,8 +847,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   // canvas columns [cfl, cfh) lie inside the frame; taps outside read zeros (BORDER_CONSTANT / zero padding), which is
   // the same as giving them weight +0 -- so only the in-frame part of a row is ever fetched
   const int cfl = is_warp ? 0 : max(0, -x0), cfh = is_warp ? cw : min(cw, sw - x0);
-  const uint32_t rowbuf32 = smem_u32(rowbuf), bars32 = smem_u32(bars);
-  uint32_t parity = 0;  // bit s: phase parity the next wait on ring slot s expects
+  const uint32_t rowbuf32 = smem_u32(rowbuf);
   for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
     const int gcols = min(32 * RMAX, ow - g0);
     const int glast = g0 + gcols - 1;
@@ -867,7 +878,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     const int last = dy_end - 1;
     const int R0 = T.start[ow + dy_begin];
     const int R1 = T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
-    // rows [f_lo, f_hi] are read by bulk copies
+    // rows [f_lo, f_hi] are fetched asynchronously
     int f_lo = INT_MAX, f_hi = INT_MIN;
     if (!is_warp && seg_bytes > 0) {
       const bool last_ok = x0 + seg_hi + 16 <= sw;  // the 16-byte-granular copy of the frame's last row stays inside it
@@ -885,22 +896,20 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     int s = 0;
     uint32_t slot32 = rowbuf32;
     uintptr_t ga = reinterpret_cast<uintptr_t>(src) + (ptrdiff_t)(y0 + R0) * pitch + (x0 + seg_lo);
-    auto issue = [&](int slot, uintptr_t g) {  // one lane
-      const uint32_t shift = (uint32_t)(g & 15), bytes = (shift + (uint32_t)seg_bytes + 15u) & ~15u;
-      const uint32_t bar = bars32 + 8u * slot, dst = rowbuf32 + (uint32_t)(slot * slot_bytes);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                   "l"(g - shift), "r"(bytes), "r"(bar)
-                   : "memory");
+    // one commit group per row, in row order (an empty group for rows that are not fetched): when row r is consumed,
+    // the groups of rows <= r + D - 1 have been committed, so "all but the D - 1 newest complete" means row r has landed
+    auto issue = [&](int slot, uintptr_t g, bool fetch) {  // whole warp: 16 bytes per lane
+      if (fetch) {
+        const uint32_t shift = (uint32_t)(g & 15), nvec = (shift + (uint32_t)seg_bytes + 15u) >> 4;
+        const uint32_t dst = rowbuf32 + (uint32_t)(slot * slot_bytes);
+        for (uint32_t v = lane; v < nvec; v += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * v), "l"(g - shift + 16u * v) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     __syncwarp();
-    if (lane == 0 && f_lo <= f_hi) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      for (int i = 0; i < D; ++i)
-        if (R0 + i >= f_lo && R0 + i <= f_hi) issue(i, ga + (ptrdiff_t)i * pitch);
-    }
+    for (int i = 0; i < D; ++i) issue(i, ga + (ptrdiff_t)i * pitch, R0 + i >= f_lo && R0 + i <= f_hi);
 
-    bool generic_write = false;
     for (int r = R0; r <= R1; ++r) {
       float h[RMAX];
       const int sy = y0 + r;
@@ -912,8 +921,8 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
         hrow<K>(rowbuf32 - seg_lo, xoff, w, h);
       } else if (is_warp) {  // (compile-time split: the branches below are the crop variant)
       } else if (r >= f_lo && r <= f_hi) {
-        mbar_wait(bars32 + 8u * s, (parity >> s) & 1u);
-        parity ^= 1u << s;
+        cp_async_wait_pending(D - 1);
+        __syncwarp();  // every lane's 16 bytes of the row are in
         hrow<K>(slot32 + ((uint32_t)ga & 15u) - seg_lo, xoff, w, h);
       } else if (sy < 0 || sy >= sh) {
         zero_row = true;
@@ -922,7 +931,6 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
         stage_crop_row(P, r, seg_lo, seg_hi, rowbuf + s * slot_bytes, lane);
         __syncwarp();
         hrow<K>(slot32 - seg_lo, xoff, w, h);
-        generic_write = true;
       }
       if (zero_row) {
 #pragma unroll
@@ -942,15 +950,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
           if (fin == 0) q = cvt_rni_sat_u8(acc[j]);
           else if (fin == 1) q = (uint32_t)(((int)acc[j] + 2) >> 2);
           else q = cvt_rni_sat_u8(__fmul_rn(acc[j], inv_area));
-          if (tcol[j] >= 0) {
-            if (cl == 1) {
-              tile[tcol[j] + trow] = (uint8_t)q;
-            } else {
-#pragma unroll
-              for (int c = 0; c < MAX_CLUSTER; ++c)
-                if (c < cl) st_cluster_u8(tile_c[c] + (uint32_t)(tcol[j] + trow), q);
-            }
-          }
+          if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)q;
         }
         ++dy;
         k = 0;
@@ -962,12 +962,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
       if (!is_warp) {
         // the slot of row r is free again: refill it with row r + D
         __syncwarp();
-        if (lane == 0 && r + D >= f_lo && r + D <= f_hi) {
-          // (the slot was last read through the generic proxy; its reads were consumed above.  A slot that was WRITTEN
-          // by generic stores needs the proxy fence before the async engine may overwrite it.)
-          if (generic_write) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue(s, ga + (ptrdiff_t)D * pitch);
-        }
+        issue(s, ga + (ptrdiff_t)D * pitch, r + D >= f_lo && r + D <= f_hi);
         ga += pitch;
         if (++s == D) s = 0;
         slot32 = rowbuf32 + (uint32_t)(s * slot_bytes);
@@ -1042,7 +1037,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   uint32_t cr_u, cl_u;
   cluster_info(cr_u, cl_u);
   const int cr = (int)cr_u, cl = (int)cl_u;  // rank in / size of the cluster that shares this sample
-  const int b = blockIdx.x / cl;
+  // launch order -> sample: the caller may schedule expensive samples (rotated, blurred) first so that the cheap ones
+  // fill the tail of the grid
+  const int b = a.order ? a.order[blockIdx.x / cl] : (int)(blockIdx.x / cl);
   const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SmemLayout L = smem_layout(ow, oh, cap);
@@ -1062,6 +1059,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   int2* dtab = reinterpret_cast<int2*>(smem + L.off_dtab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
   float* lab = reinterpret_cast<float*>(smem + L.off_lab);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.off_bars) + NWARPS * RING_MAX;  // cluster exchange barrier
 
   trace_mark(a, 0);
   if (a.trace_out && tid == 0) {
@@ -1071,6 +1069,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   }
   if (lane == 0) {
     for (int s = 0; s < RING_MAX; ++s) mbar_init(&bars[s], 1);
+    if (warp == 0) mbar_init(xbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // ---- label data of this sample -> shared memory (overlaps the plan; labels do not depend on it) ----------
@@ -1161,6 +1160,18 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   __syncthreads();
 
   trace_mark(a, 1);
+  // this CTA's band of output rows, and the bytes the other CTAs of the cluster will bulk-copy into this tile
+  const int rows_lo = (cr * oh) / cl, rows_hi = ((cr + 1) * oh) / cl;
+  int rx_bytes = 0;
+  if (cl > 1 && P.status == B200AUG_S_OK && P.rot_dir == 0) {
+    for (int q = 0; q < cl; ++q) {
+      if (q == cr) continue;
+      const int lo = ((q * oh) / cl) * ow, hi = (((q + 1) * oh) / cl) * ow, alo = min((lo + 15) & ~15, hi), ahi = max(hi & ~15, alo);
+      rx_bytes += ahi - alo;
+    }
+    if (tid == 0 && rx_bytes)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(xbar)), "r"(rx_bytes) : "memory");
+  }
   if (tid == 0 && a.status_out) a.status_out[b] = P.status;
   if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
 
@@ -1249,18 +1260,44 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
 #undef B200AUG_BAND
   } else if (P.status == B200AUG_S_OK) {
     // per-pixel path: integer-factor area, linear up-scaling, plain copy, very wide taps / canvases
-    uint32_t tile_c[MAX_CLUSTER];
-#pragma unroll
-    for (int q = 0; q < MAX_CLUSTER; ++q) tile_c[q] = map_to_rank(smem_u32(tile), min(q, cl - 1));
-    for (int p = (cr * npix) / cl + tid; p < ((cr + 1) * npix) / cl; p += NTHREADS) {
+    for (int p = rows_lo * ow + tid; p < rows_hi * ow; p += NTHREADS) {
       const int dy = p / ow, dx = p - dy * ow;
-      const uint32_t v = scalar_out_px(P, T, ow, dx, dy);
-#pragma unroll
-      for (int c = 0; c < MAX_CLUSTER; ++c)
-        if (c < cl) st_cluster_u8(tile_c[c] + (uint32_t)(tm.o + dy * tm.sa + dx * tm.sb), v);
+      tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
     }
   } else {
     for (int p = tid; p < npix; p += NTHREADS) tile[p] = 0;
+  }
+  // ---- cluster exchange: every CTA resampled a band of rows into its own tile; now each sends its band to the others.
+  // Without a 90-degree rotation the band is a contiguous byte range of the tile: its 16-byte aligned interior goes as
+  // one bulk copy through distributed shared memory (completing on the receiver's mbarrier), the ragged ends as byte
+  // stores.  Rotated-by-90 samples (1 %) send pixel by pixel.
+  if (cl > 1 && P.status == B200AUG_S_OK) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tile writes (generic proxy) before the bulk copy reads them
+    __syncthreads();
+    const uint32_t tile32 = smem_u32(tile), xbar32 = smem_u32(xbar);
+    if (P.rot_dir == 0) {
+      const int lo = rows_lo * ow, hi = rows_hi * ow, alo = min((lo + 15) & ~15, hi), ahi = max(hi & ~15, alo);
+      for (int q = 0; q < cl; ++q) {
+        if (q == cr) continue;
+        const uint32_t rt = map_to_rank(tile32, q);
+        if (tid == 0 && ahi > alo)
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rt + alo),
+                       "r"(tile32 + alo), "r"(ahi - alo), "r"(map_to_rank(xbar32, q))
+                       : "memory");
+        for (int i = lo + tid; i < alo; i += NTHREADS) st_cluster_u8(rt + i, tile[i]);
+        for (int i = ahi + tid; i < hi; i += NTHREADS) st_cluster_u8(rt + i, tile[i]);
+      }
+    } else {
+      for (int q = 0; q < cl; ++q) {
+        if (q == cr) continue;
+        const uint32_t rt = map_to_rank(tile32, q);
+        for (int p = rows_lo * ow + tid; p < rows_hi * ow; p += NTHREADS) {
+          const int dy = p / ow, dx = p - dy * ow, idx = tm.o + dy * tm.sa + dx * tm.sb;
+          st_cluster_u8(rt + idx, tile[idx]);
+        }
+      }
+    }
+    if (rx_bytes) mbar_wait(xbar32, 0);  // the other CTAs' bands have landed in this tile
   }
   cluster_sync(cl);  // every CTA's tile now holds the whole crop; no distributed-shared-memory access after this point
   trace_mark(a, 3);

@@ -175,9 +175,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
   float u1 = (float)((xa >> 8) + 1u) * 5.9604644775390625e-08f;  // (0, 1]
   float u2 = (float)(xb >> 8) * 5.9604644775390625e-08f;         // [0, 1)
-  float r = sqrtf(-2.0f * logf(u1));
+  // hardware approximations (lg2 / sqrt / sin / cos units): the noise only has to match the oracle's float32 Box-Muller
+  // to well within the 1/255 pixel tolerance (worst case ~1e-4 of a grey level at the largest noise std)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c;
   z1 = r * s;
 }

@@ -42,7 +42,7 @@ class FusedArgs(C.Structure):
                 ("fields", Field * MAX_FIELDS),
                 ("view_roi_out", C.c_void_p), ("tr_out", C.c_void_p), ("backtransform_out", C.c_void_p),
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),
-                ("trace_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_stride", C.c_int64),
+                ("trace_out", C.c_void_p), ("order", C.c_void_p), ("workspace", C.c_void_p), ("workspace_stride", C.c_int64),
                 ("photo", PhotoParams)]
 
 

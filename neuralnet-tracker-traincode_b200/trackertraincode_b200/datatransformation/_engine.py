@@ -174,6 +174,26 @@ def _workspace(device, B: int):
     return ws, stride
 
 
+def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams]) -> Optional[torch.Tensor]:
+    """Most expensive samples first (B200AugFusedArgs.order).  Only parameters that are still on the host are looked at
+    -- this never synchronises with the device; returns None when nothing distinguishes the samples."""
+    cost = torch.zeros(B)
+    known = False
+    if geo is not None and not geo.angles.is_cuda:
+        cost += (geo.angles.reshape(B) != 0).float() * 1.0  # warpAffine stage
+        known = True
+    if photo is not None and not torch.as_tensor(photo.apply).is_cuda:
+        ap = torch.as_tensor(photo.apply).reshape(B, N.NUM_OPS).bool()
+        chosen = torch.zeros(N.NUM_OPS, dtype=torch.bool)
+        chosen[list(photo.order)] = True
+        cost += (ap[:, 5] & chosen[5]).float() * 1.2 + (ap[:, 0] & chosen[0]).float() * 0.2
+        cost += torch.as_tensor(photo.noise_apply).reshape(B, N.NUM_NOISE).float().sum(1) * 0.25
+        known = True
+    if not known or float(cost.max()) == 0.0:
+        return None
+    return torch.argsort(cost, descending=True, stable=True).to(torch.int32)
+
+
 def fused_forward(batch: Batch, **kw) -> FusedResult:
     """Run the stages selected by `flags` on every field of `batch` in one kernel launch; returns a new Batch."""
     call = prepare_fused(batch, **kw)
@@ -186,7 +206,8 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   photo: Optional[PhotoParams] = None, roi_variable: str = "roi", landmark_variable: str = "pt3d_68",
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
-                  want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0) -> PreparedCall:
+                  want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0,
+                  schedule: bool = True) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -306,6 +327,12 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
             args.image_u8_out = img_out.data_ptr()
 
     view_roi = tr = status = None
+    if schedule and image_keys and B > 1:
+        order = launch_order(B, geo if (flags & N.F_FOCUS) else None, photo if (flags & N.F_PHOTOMETRIC) else None)
+        if order is not None:
+            od = order.to(device, non_blocking=True)
+            keep.append(od)
+            args.order = od.data_ptr()
     if (flags & N.F_FOCUS) and image_keys and use_workspace:
         ws, stride = _workspace(device, B)
         args.workspace, args.workspace_stride = ws.data_ptr(), stride

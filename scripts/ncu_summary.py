@@ -54,3 +54,31 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
 print("--- by stall samples")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{k[0]}:{k[1]:4d} inst {a[0] / tot * 100:5.1f}% samp {a[1] / ts * 100:5.1f}%  {a[2][:110]}")
+
+# ---- instructions / stall samples per enclosing function of the kernel source
+import re
+src_path = None
+for k in agg:
+    if k[0] and k[0].endswith("b200aug_fused.cu"):
+        src_path = k[0]
+import os
+cu = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neuralnet-tracker-traincode_b200", "csrc", "b200aug_fused.cu")
+if os.path.exists(cu):
+    lines = open(cu).read().split("\n")
+    func_at = []
+    cur_f = "(top)"
+    pat = re.compile(r"^(?:template.*\n)?(?:__device__|__global__|static|extern)[^;{]*?\b([A-Za-z_0-9]+)\s*\(")
+    for i, ln in enumerate(lines, 1):
+        m = re.match(r"^(?:__device__|__global__)[^;]*?\b([A-Za-z_0-9]+)\s*\(", ln)
+        if m and not ln.startswith(" "):
+            cur_f = m.group(1)
+        func_at.append(cur_f)
+    per = collections.Counter()
+    pers = collections.Counter()
+    for (f, l), a in agg.items():
+        name = func_at[l - 1] if f == "b200aug_fused.cu" and 0 < l <= len(func_at) else f
+        per[name] += a[0]
+        pers[name] += a[1]
+    print("--- by function (lines of b200aug_fused.cu; inlined callees count where they are written)")
+    for name, v in per.most_common(25):
+        print(f"{name:32s} inst {v / tot * 100:5.1f}%  samples {pers[name] / ts * 100:5.1f}%")
