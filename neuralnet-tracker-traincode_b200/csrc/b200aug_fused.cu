@@ -36,6 +36,7 @@ constexpr int DT_CAP = 512;        // widest warp canvas with per-column delta t
 constexpr int DEFAULT_ROWBUF = 2560;  // per-warp staging bytes: a ring of up to RING_MAX crop rows in flight, or one
                                       // staged warpAffine tile footprint (39 rows x 64 B)
 constexpr int RING_MAX = 8;
+constexpr int ROWPROG_CAP = 96;    // canvas rows one warp can stream per band (its vertical-pass program, 8 B per row)
 constexpr int DEFAULT_CLUSTER = 2;  // CTAs sharing one sample
 constexpr int LAB_CAP = 1024;      // floats of label data staged in shared memory while the plan is being built
 
@@ -72,7 +73,7 @@ struct Plan {
 };
 
 struct SmemLayout {
-  size_t off_tabs, off_tile, off_rowbuf, off_dtab, off_bars, off_lab, total;
+  size_t off_tabs, off_tile, off_rowbuf, off_dtab, off_bars, off_lab, off_prog, total;
   int ntab;
 };
 
@@ -95,6 +96,8 @@ __host__ __device__ inline SmemLayout smem_layout(int ow, int oh, int cap) {
   o += (size_t)(NWARPS * RING_MAX + 2) * sizeof(uint64_t);  // ring barriers + the cluster exchange barrier
   L.off_lab = o;
   o += (size_t)LAB_CAP * sizeof(float);
+  L.off_prog = o;
+  o += (size_t)NWARPS * ROWPROG_CAP * sizeof(float2);
   L.total = o;
   return L;
 }
@@ -848,6 +851,34 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   // the same as giving them weight +0 -- so only the in-frame part of a row is ever fetched
   const int cfl = is_warp ? 0 : max(0, -x0), cfh = is_warp ? cw : min(cw, sw - x0);
   const uint32_t rowbuf32 = smem_u32(rowbuf);
+
+  // ---- vertical-pass program of this warp's band: for canvas row R0 + i, prog[i] = (+-beta_a, beta_b):
+  //   acc += beta_a * h;  if beta_a carries a minus sign the output row is complete: store it, move to the next output
+  //   row and restart its sum as beta_b * h (beta_b != 0 only when this canvas row is also the next row's first tap).
+  // Built once (lanes = rows) from cv2's per-axis table, so the streaming loop below has no table logic left in it.
+  const int last = dy_end - 1;
+  const int R0 = T.start[ow + dy_begin];
+  const int R1 = T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
+  float2* const prog = reinterpret_cast<float2*>(smem + L.off_prog) + warp * ROWPROG_CAP;
+  for (int i = lane; i <= R1 - R0; i += 32) {
+    const int r = R0 + i;
+    int d = dy_begin;
+    while (d < last && T.start[ow + d] + (T.n[ow + d] & 0xffff) - 1 < r) ++d;
+    const int nf = T.n[ow + d], yn = nf & 0xffff, k = r - T.start[ow + d];
+    float ba = 0.f, bb = 0.f;
+    bool emit = false;
+    if (k >= 0 && k < yn) {
+      ba = area_alpha(k, yn, nf & (1 << 30), nf & (1u << 31), T.a[ow + d], T.b[ow + d], T.c[ow + d]);
+      emit = (k == yn - 1);
+      if (emit && d < last && T.start[ow + d + 1] == r) {
+        const int nf2 = T.n[ow + d + 1];
+        bb = area_alpha(0, nf2 & 0xffff, nf2 & (1 << 30), nf2 & (1u << 31), T.a[ow + d + 1], T.b[ow + d + 1], T.c[ow + d + 1]);
+      }
+    }
+    prog[i] = make_float2(emit ? -ba : ba, bb);
+  }
+  __syncwarp();
+
   for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
     const int gcols = min(32 * RMAX, ow - g0);
     const int glast = g0 + gcols - 1;
@@ -875,9 +906,6 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     const int slot_bytes = (seg_bytes + 15 + 15 + ROWBUF_SLACK) & ~15;
     const int D = max(1, min(RING_MAX, (cap + ROWBUF_SLACK) / slot_bytes));
 
-    const int last = dy_end - 1;
-    const int R0 = T.start[ow + dy_begin];
-    const int R1 = T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
     // rows [f_lo, f_hi] are fetched asynchronously
     int f_lo = INT_MAX, f_hi = INT_MIN;
     if (!is_warp && seg_bytes > 0) {
@@ -885,9 +913,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
       f_lo = max(R0, -y0);
       f_hi = min(R1, (last_ok ? sh - 1 : sh - 2) - y0);
     }
-    int dy = dy_begin, k = 0;
-    int ys = T.start[ow + dy], ynf = T.n[ow + dy];
-    float yaf = T.a[ow + dy], yam = T.b[ow + dy], yal = T.c[ow + dy];
+    int trow = dy_begin * tm.sa;  // tile offset of the output row being accumulated
     float acc[RMAX];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) acc[j] = 0.f;
@@ -936,14 +962,12 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
 #pragma unroll
         for (int j = 0; j < RMAX; ++j) h[j] = 0.f;
       }
-      // vertical pass: this row is tap k of output row dy, and possibly tap 0 of dy + 1 as well
-      while (dy < dy_end && ys + k == r) {
-        const int yn = ynf & 0xffff;
-        const float beta = area_alpha(k, yn, ynf & (1 << 30), ynf & (1u << 31), yaf, yam, yal);
+      // vertical pass (see the program above); a fresh sum starts from +0, and 0 + x is exact
+      const float2 pr = prog[r - R0];
+      const float ba = fabsf(pr.x);
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j) acc[j] = (k == 0) ? __fmul_rn(beta, h[j]) : __fadd_rn(acc[j], __fmul_rn(beta, h[j]));
-        if (++k < yn) break;
-        const int trow = dy * tm.sa;
+      for (int j = 0; j < RMAX; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(ba, h[j]));
+      if (pr.x < 0.f) {
 #pragma unroll
         for (int j = 0; j < RMAX; ++j) {
           uint32_t q;
@@ -951,13 +975,9 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
           else if (fin == 1) q = (uint32_t)(((int)acc[j] + 2) >> 2);
           else q = cvt_rni_sat_u8(__fmul_rn(acc[j], inv_area));
           if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)q;
+          acc[j] = __fmul_rn(pr.y, h[j]);
         }
-        ++dy;
-        k = 0;
-        if (dy < dy_end) {
-          ys = T.start[ow + dy]; ynf = T.n[ow + dy];
-          yaf = T.a[ow + dy]; yam = T.b[ow + dy]; yal = T.c[ow + dy];
-        }
+        trow += tm.sa;
       }
       if (!is_warp) {
         // the slot of row r is free again: refill it with row r + D
@@ -1241,6 +1261,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   const TileMap tm = make_tile_map(P, ow, oh);
   bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) &&
               (P.src_mode != SRC_WARP || use_dtab);
+  if (fast) {
+    // a warp's band of canvas rows must fit its vertical-pass program
+    const int rows_per_warp = (rows_hi - rows_lo + NWARPS - 1) / NWARPS;
+    const int sy_ceil = (rs == RS_AREA_INT) ? P.iscale_y : (int)ceil(P.scale_y);
+    if ((rows_per_warp + 1) * sy_ceil + 2 > ROWPROG_CAP) fast = false;
+  }
   if (fast) {
     // every column group's canvas segment must fit the per-warp row buffer (only staged rows need it)
     for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
