@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200AUG_ABI_VERSION 3
+#define B200AUG_ABI_VERSION 4
 
 /* error codes */
 #define B200AUG_OK 0
@@ -179,6 +179,15 @@ int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream);
  * (tr [B,2,3], or one [2,3] broadcast when tr_stride == 0). */
 int b200aug_apply_affine2d(const float* tr, int64_t tr_stride, int batch, int n_fields, const B200AugField* fields,
                            void* stream);
+
+/* KorniaImageDistortions.__call__ on its own (batch/intensity.py:30-40 with the op lists of pipelines.py:510-527):
+ * both photometric stages on float32 images [B,1,h,w] that already live on the device (the fused kernel covers the case
+ * where they follow the crop).  Stage 1 = photo->order / apply / factors (n_order = 0 skips it); stage 2 = noise_apply
+ * (NULL skips it) + clip.  `bias` is added last (-0.5 fuses whiten_batch, batch/normalization.py:94-99; 0 otherwise).
+ * `tmp` [B,h,w] is scratch, required (and distinct from in/out) when the blur is among the ordered ops; in == out is
+ * allowed otherwise. */
+int b200aug_photometric_f32(const float* in, float* out, float* tmp, int batch, int width, int height,
+                            const B200AugPhotoParams* photo, float bias, void* stream);
 
 #ifdef __cplusplus
 }

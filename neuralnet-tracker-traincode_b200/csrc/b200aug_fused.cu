@@ -367,14 +367,13 @@ __device__ __forceinline__ Aff normalize_transform(const PlanCore& c) {
 }
 
 // branch 5: photometric parameters of this sample
-__device__ void plan_photo(const B200AugFusedArgs& a, int b, Plan& P) {
+__device__ void plan_photo(const B200AugPhotoParams& pp, bool enabled, int b, Plan& P) {
   P.n_ops = 0;
   P.blur_pos = -1;
   P.eq_pos = -1;
   P.eq_step0 = 0;
   P.any_noise = 0;
-  if (!(a.flags & B200AUG_F_PHOTOMETRIC)) return;
-  const B200AugPhotoParams& pp = a.photo;
+  if (!enabled) return;
   uint8_t op_on[B200AUG_NUM_OPS] = {0, 0, 0, 0, 0, 0}, noise_on[B200AUG_NUM_NOISE] = {0, 0, 0, 0};
   if (pp.apply)
 #pragma unroll
@@ -1172,7 +1171,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
         if (lane == 0) P.t3 = aff_derive(normalize_transform(c));
         break;
       case 5:
-        if (lane == 0) plan_photo(a, b, P);
+        if (lane == 0) plan_photo(a.photo, (a.flags & B200AUG_F_PHOTOMETRIC) != 0, b, P);
         break;
       default: break;
     }
@@ -1471,6 +1470,137 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   trace_mark(a, 4);
 }
 
+
+// ------------------------------------------------------------------------------------------------ stand-alone photometric
+
+// KorniaImageDistortions on float32 images that are already on the device (batch/intensity.py:30-40 called on its own,
+// pipelines.py:508-527): the same op semantics as the fused kernel, but on arbitrary float input, so nothing collapses
+// into a uint8 LUT.  One CTA per image; the image ping-pongs between `out` and `tmp` (both stay in L2).  Point ops are
+// deferred ("pending") and evaluated on the fly by whichever pass needs their result next: the equalize histogram, the
+// materialisation in front of the blur, or the final noise / clip pass.
+__device__ __forceinline__ float photo_f32_value(const Plan& P, const float* cur, int p, int from, int to, const float* eq_lut) {
+  return apply_point_ops(P, cur[p], from, to, eq_lut);
+}
+
+__global__ void __launch_bounds__(NTHREADS) photometric_f32_kernel(const float* in, float* out, float* tmp,
+                                                                   int w, int h, const __grid_constant__ B200AugPhotoParams pp,
+                                                                   float bias) {
+  __shared__ Plan P;
+  __shared__ float eq_lut[256];
+  __shared__ unsigned binhist[256];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, npix = w * h;
+  const float* src = in + (size_t)b * npix;
+  float* A = out + (size_t)b * npix;
+  float* B = tmp ? tmp + (size_t)b * npix : nullptr;
+  if (tid == 0) plan_photo(pp, true, b, P);
+  __syncthreads();
+  const float* cur = src;
+  int from = 0;  // ops [from, k) are pending on `cur`
+  for (int k = 0; k < P.n_ops; ++k) {
+    const int op = P.ops[k];
+    if (op == B200AUG_OP_EQUALIZE) {
+      binhist[tid] = 0;
+      __syncthreads();
+      for (int p = tid; p < npix; p += NTHREADS) {
+        const float x = photo_f32_value(P, cur, p, from, k, eq_lut);
+        const float im = __fmul_rn(x, 255.f);
+        if (im >= 0.f && im <= 255.f) atomicAdd(&binhist[eq_bin(x)], 1u);  // torch.histc ignores out-of-range values
+      }
+      __syncthreads();
+      if (warp == 0) {
+        unsigned loc[8], run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = binhist[lane * 8 + i]; run += loc[i]; }
+        unsigned incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        int my_last = -1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (loc[i]) my_last = lane * 8 + i;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_last = max(my_last, __shfl_xor_sync(0xffffffffu, my_last, o));
+        const unsigned last_nz = (my_last >= 0) ? binhist[my_last] : 0u;
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned step = (total - last_nz) / 255u;
+        if (lane == 0) P.eq_step0 = (step == 0);
+        if (step) {
+          unsigned c = incl - run;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int bin = lane * 8 + i;
+            eq_lut[bin] = (bin == 0) ? 0.f : (float)min((c + step / 2u) / step, 255u);
+            c += loc[i];
+          }
+        }
+      }
+      __syncthreads();  // from here on op k is a point op like the others
+    } else if (op == B200AUG_OP_BLUR) {
+      // materialise the pending ops, then the separable 5x5 (horizontal pass inside the vertical one, same order of
+      // float operations as two full passes)
+      float* M = (cur == A) ? B : A;
+      for (int p = tid; p < npix; p += NTHREADS) M[p] = photo_f32_value(P, cur, p, from, k, eq_lut);
+      __syncthreads();
+      float* D = (M == A) ? B : A;
+      const float g[5] = {0x1.ebd752p-4f, 0x1.defcdep-3f, 0x1.2b1778p-2f, 0x1.defcdep-3f, 0x1.ebd752p-4f};
+      for (int p = tid; p < npix; p += NTHREADS) {
+        const int y = p / w, x = p - y * w;
+        int xs[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) xs[i] = reflect_idx(x + i - 2, w);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const float* row = M + reflect_idx(y + j - 2, h) * w;
+          float t = __fmul_rn(g[0], row[xs[0]]);
+#pragma unroll
+          for (int i = 1; i < 5; ++i) t = __fadd_rn(t, __fmul_rn(g[i], row[xs[i]]));
+          acc = (j == 0) ? __fmul_rn(g[0], t) : __fadd_rn(acc, __fmul_rn(g[j], t));
+        }
+        D[p] = acc;
+      }
+      __syncthreads();
+      cur = D;
+      from = k + 1;
+    }
+  }
+  // final pass: pending point ops, the noise stages, clip, bias (whiten), in the quad layout of the Philox stream
+  const int Q = (npix + 3) >> 2;
+  const uint64_t sid = pp.sample_offset + (uint64_t)b;
+  const uint2 key = make_uint2((uint32_t)pp.seed, (uint32_t)(pp.seed >> 32));
+  for (int g = tid; g < Q; g += NTHREADS) {
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = g + i * Q;
+      x[i] = (p < npix) ? photo_f32_value(P, cur, p, from, P.n_ops, eq_lut) : 0.f;
+    }
+    if (P.any_noise) {
+#pragma unroll
+      for (int s = 0; s < B200AUG_NUM_NOISE; ++s) {
+        if (!P.noise_on[s]) continue;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)s, (uint32_t)sid, 0x6E6F6973u), key);
+        float z[4];
+        box_muller(r.x, r.y, z[0], z[1]);
+        box_muller(r.z, r.w, z[2], z[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = __fadd_rn(x[i], __fmul_rn(pp.noise_std[s], z[i]));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = g + i * Q;
+      if (p < npix) {
+        float v = x[i];
+        if (pp.clip) v = fminf(fmaxf(v, 0.f), 1.f);
+        A[p] = __fadd_rn(v, bias);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ apply_affine2d
 
 __global__ void apply_affine2d_kernel(const float* __restrict__ tr, int64_t tr_stride, int n_fields,
@@ -1618,6 +1748,24 @@ extern "C" int b200aug_apply_affine2d(const float* tr, int64_t tr_stride, int ba
   B200AugField f[B200AUG_MAX_FIELDS] = {};
   for (int i = 0; i < n_fields; ++i) f[i] = fields[i];
   apply_affine2d_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(tr, tr_stride, n_fields, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  return B200AUG_OK;
+}
+
+extern "C" int b200aug_photometric_f32(const float* in, float* out, float* tmp, int batch, int width, int height,
+                                       const B200AugPhotoParams* photo, float bias, void* stream) {
+  if (!in || !out || !photo || batch < 0 || width <= 0 || height <= 0) return B200AUG_E_INVALID_ARG;
+  if (photo->n_order < 0 || photo->n_order > B200AUG_NUM_OPS || (photo->n_order > 0 && !photo->apply)) return B200AUG_E_INVALID_ARG;
+  bool blur = false;
+  for (int k = 0; k < photo->n_order; ++k) {
+    if (photo->order[k] < 0 || photo->order[k] >= B200AUG_NUM_OPS) return B200AUG_E_INVALID_ARG;
+    blur = blur || photo->order[k] == B200AUG_OP_BLUR;
+  }
+  if (blur && (!tmp || tmp == out || tmp == in)) return B200AUG_E_INVALID_ARG;  // the blur ping-pongs between out and tmp
+  if (blur && in == out) return B200AUG_E_INVALID_ARG;
+  if (batch == 0) return B200AUG_OK;
+  photometric_f32_kernel<<<batch, NTHREADS, 0, (cudaStream_t)stream>>>(in, out, tmp, width, height, *photo, bias);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
   return B200AUG_OK;

@@ -8,12 +8,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200aug.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_FIELDS, NUM_OPS, NUM_NOISE = 8, 6, 4
 
 F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN = 1, 2, 4, 8, 16, 32, 64
 CAT_GENERAL, CAT_QUAT, CAT_XYS, CAT_ROI, CAT_POINTS = 0, 1, 2, 3, 4
 S_OK, S_EMPTY_BOX, S_UNSUPPORTED, S_ROWBUF = 0, 1, 2, 3
+OP_EQUALIZE, OP_POSTERIZE, OP_GAMMA, OP_CONTRAST, OP_BRIGHTNESS, OP_BLUR = range(6)
 
 
 class Src(C.Structure):
@@ -47,7 +48,7 @@ class FusedArgs(C.Structure):
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_fused_forward", "b200aug_apply_affine2d")
+           "b200aug_workspace_stride", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32")
 
 
 class NativeError(RuntimeError):
@@ -71,6 +72,9 @@ def _load():
     lib.b200aug_fused_forward.argtypes = [C.POINTER(FusedArgs), C.c_void_p]
     lib.b200aug_apply_affine2d.restype = C.c_int
     lib.b200aug_apply_affine2d.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(Field), C.c_void_p]
+    lib.b200aug_photometric_f32.restype = C.c_int
+    lib.b200aug_photometric_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(PhotoParams),
+                                            C.c_float, C.c_void_p]
     if lib.b200aug_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {lib.b200aug_abi_version()} vs binding {ABI_VERSION}")
     return lib

@@ -194,6 +194,27 @@ def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams])
     return torch.argsort(cost, descending=True, stable=True).to(torch.int32)
 
 
+def marshal_photo(photo: PhotoParams, B: int, device) -> Tuple[Any, List[Any]]:
+    """PhotoParams -> the C struct B200AugPhotoParams (device arrays uploaded); returns (struct, tensors to keep alive)."""
+    f32, u8 = torch.float32, torch.uint8
+    p = N.PhotoParams()
+    p.n_order = len(photo.order)
+    for i, op in enumerate(photo.order):
+        p.order[i] = int(op)
+    p.clip = int(photo.clip)
+    ap = _dev(photo.apply, device, u8).reshape(B, N.NUM_OPS)
+    bi = _dev(photo.bits, device, torch.int32).reshape(B)
+    ga = _dev(photo.gamma, device, f32).reshape(B)
+    co = _dev(photo.contrast, device, f32).reshape(B)
+    br = _dev(photo.brightness, device, f32).reshape(B)
+    na = _dev(photo.noise_apply, device, u8).reshape(B, N.NUM_NOISE)
+    p.apply, p.bits, p.gamma, p.contrast, p.brightness, p.noise_apply = (t.data_ptr() for t in (ap, bi, ga, co, br, na))
+    for i, s in enumerate(photo.noise_std):
+        p.noise_std[i] = float(s)
+    p.seed, p.sample_offset = int(photo.seed) & (2**64 - 1), int(photo.sample_offset)
+    return p, [ap, bi, ga, co, br, na]
+
+
 def fused_forward(batch: Batch, **kw) -> FusedResult:
     """Run the stages selected by `flags` on every field of `batch` in one kernel launch; returns a new Batch."""
     call = prepare_fused(batch, **kw)
@@ -290,22 +311,8 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
             args.rot_dir = rd.data_ptr()
     if flags & N.F_PHOTOMETRIC:
         assert photo is not None
-        p = args.photo
-        p.n_order = len(photo.order)
-        for i, op in enumerate(photo.order):
-            p.order[i] = int(op)
-        p.clip = int(photo.clip)
-        ap = _dev(photo.apply, device, u8).reshape(B, N.NUM_OPS)
-        bi = _dev(photo.bits, device, torch.int32).reshape(B)
-        ga = _dev(photo.gamma, device, f32).reshape(B)
-        co = _dev(photo.contrast, device, f32).reshape(B)
-        br = _dev(photo.brightness, device, f32).reshape(B)
-        na = _dev(photo.noise_apply, device, u8).reshape(B, N.NUM_NOISE)
-        keep += [ap, bi, ga, co, br, na]
-        p.apply, p.bits, p.gamma, p.contrast, p.brightness, p.noise_apply = (t.data_ptr() for t in (ap, bi, ga, co, br, na))
-        for i, s in enumerate(photo.noise_std):
-            p.noise_std[i] = float(s)
-        p.seed, p.sample_offset = int(photo.seed) & (2**64 - 1), int(photo.sample_offset)
+        args.photo, pk = marshal_photo(photo, B, device)
+        keep += pk
 
     # ---- image
     img_out = None
