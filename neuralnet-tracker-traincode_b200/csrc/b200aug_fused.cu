@@ -1006,7 +1006,10 @@ __device__ float apply_point_ops(const Plan& P, float x, int from, int to, const
         int sh = 8 - P.bits;
         x = __fdiv_rn((float)((q >> sh) << sh), 255.f);
       } break;
-      case B200AUG_OP_GAMMA: x = fminf(fmaxf(powf(x, P.gamma), 0.f), 1.f); break;
+      case B200AUG_OP_GAMMA: {
+        const float pw = powf(x, P.gamma);
+        x = (pw != pw) ? pw : fminf(fmaxf(pw, 0.f), 1.f);  // torch.clamp propagates the NaN of pow(negative, g); fmaxf would not
+      } break;
       case B200AUG_OP_CONTRAST: x = fminf(fmaxf(__fmul_rn(x, P.contrast), 0.f), 1.f); break;
       case B200AUG_OP_BRIGHTNESS: x = fminf(fmaxf(__fadd_rn(x, P.brightness_shift), 0.f), 1.f); break;
       default: break;
@@ -1050,7 +1053,7 @@ __device__ float blurred_value(const uint8_t* tile, const float* lut, int ow, in
 
 // ------------------------------------------------------------------------------------------------ the kernel
 
-__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap) {
+__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap, int lay_w, int lay_h) {
   const B200AugFusedArgs& a = K.a;
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t cr_u, cl_u;
@@ -1061,7 +1064,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   const int b = a.order ? a.order[blockIdx.x / cl] : (int)(blockIdx.x / cl);
   const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const SmemLayout L = smem_layout(ow, oh, cap);
+  // (lay_w, lay_h) = (out_w, out_h) when an image is produced; label-only launches use a 1 x 1 layout so that label
+  // frames of any size (normalize_batch on 640 x 480 labels) never hit the shared-memory budget
+  const SmemLayout L = smem_layout(lay_w, lay_h, cap);
   Plan& P = *reinterpret_cast<Plan*>(smem);
   float* lut = reinterpret_cast<float*>(smem + ((sizeof(Plan) + 15) & ~size_t(15)));
   float* eq_lut = lut + 256;
@@ -1594,7 +1599,7 @@ __global__ void __launch_bounds__(NTHREADS) photometric_f32_kernel(const float* 
       const int p = g + i * Q;
       if (p < npix) {
         float v = x[i];
-        if (pp.clip) v = fminf(fmaxf(v, 0.f), 1.f);
+        if (pp.clip && v == v) v = fminf(fmaxf(v, 0.f), 1.f);  // (torch.clip keeps a NaN; arbitrary float input can carry one)
         A[p] = __fadd_rn(v, bias);
       }
     }
@@ -1713,7 +1718,9 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
 
   int cap = a.rowbuf_capacity > 0 ? a.rowbuf_capacity : DEFAULT_ROWBUF;
   cap = (cap + 15) & ~15;
-  const size_t smem = smem_layout(a.out_w, a.out_h, cap).total;
+  const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
+  const int lay_w = want_image ? a.out_w : 1, lay_h = want_image ? a.out_h : 1;
+  const size_t smem = smem_layout(lay_w, lay_h, cap).total;
   if (smem > 227 * 1024) return B200AUG_E_SMEM;
   cudaError_t e = cudaFuncSetAttribute(fused_augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
@@ -1733,7 +1740,7 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, fused_augment_kernel, K, cap);
+  e = cudaLaunchKernelEx(&cfg, fused_augment_kernel, K, cap, lay_w, lay_h);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
   return B200AUG_OK;

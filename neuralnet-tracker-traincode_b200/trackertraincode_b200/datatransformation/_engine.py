@@ -333,6 +333,11 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
             img_out = torch.empty((B, 1, oh, ow), dtype=u8, device=device)
             args.image_u8_out = img_out.data_ptr()
 
+    else:
+        # label-only call: the label frame (normalize / flip need W and H) comes from the metadata
+        w_, h_ = meta.image_wh
+        args.src_uniform = N.Src(None, int(w_), int(h_), int(w_), 0)
+
     view_roi = tr = status = None
     if schedule and image_keys and B > 1:
         order = launch_order(B, geo if (flags & N.F_FOCUS) else None, photo if (flags & N.F_PHOTOMETRIC) else None)

@@ -41,15 +41,29 @@ def test_photometric_f32_vs_oracle(hw):
         pp.order = order
         pp.apply[:] = True
         pp.apply[n - 1] = False  # one untouched sample
+        pp.apply[3, 2] = False  # no gamma on the sample with negative values (pow -> NaN, which then poisons blur / equalize)
         pp.noise_apply[:] = False
         if k % 2:
             pp.noise_apply[:, k % 4] = True
         pp.clip = bool(k % 3)
         want = opho.photometric_batch(x, pp)
         got = dtb.photometric_f32(torch.from_numpy(x).cuda(), _photo(E, pp)).cpu().numpy()
-        err = np.abs(got - want).reshape(n, -1).max(1)
-        assert err.max() <= 2e-4, f"order {order}: {err}"
-        assert np.median(err) <= 3e-5
+        assert not np.isnan(got).any() and not np.isnan(want).any()
+        err = np.abs(got - want).reshape(n, -1)
+        if 0 in order and order.index(0) > 0 and (2 in order[:order.index(0)]):
+            # equalize is a step function: a 1-ulp difference of powf() in front of it moves a pixel across a histogram
+            # bin edge now and then, which shifts that pixel by a few grey levels.  Bound how often and by how much.
+            assert (err > 2e-4).mean() < 2e-3 and err.max() <= 12.0 / 255, f"order {order}: {(err > 2e-4).mean()} {err.max()}"
+        else:
+            assert err.max() <= 2e-4, f"order {order}: {err.max(1)}"
+        assert np.median(err.max(1)) <= 3e-5
+    # NaN semantics of torch.pow / torch.clamp on negative input are kept by the stand-alone kernel
+    pp = opho.sample_photo_params(rng, n, seed=9)
+    pp.order, pp.apply[:], pp.noise_apply[:] = [2], True, False
+    with np.errstate(invalid="ignore"):
+        want = opho.photometric_batch(x, pp)
+    got = dtb.photometric_f32(torch.from_numpy(x).cuda(), _photo(E, pp)).cpu().numpy()
+    assert np.isnan(want[3]).any() and np.array_equal(np.isnan(got), np.isnan(want))
     # bias fuses whiten_batch; in-place (in == out) is allowed without blur
     pp = opho.sample_photo_params(rng, n, seed=3)
     pp.order, pp.apply[:], pp.noise_apply[:] = [3, 4], True, False
