@@ -114,7 +114,7 @@ typedef struct B200AugFusedArgs {
   int32_t batch;
   int32_t out_w, out_h;         /* crop size (129 x 129 for the pose net) */
   uint32_t flags;               /* B200AUG_F_* */
-  int32_t rowbuf_capacity;      /* bytes of per-warp staging (ring of source rows in flight); 0 = default (2560) */
+  int32_t rowbuf_capacity;      /* bytes of per-warp staging (ring of source rows in flight); 0 = default (3584) */
 
   /* sources: a table of descriptors (ragged batch) or, if NULL, one descriptor + stride (stacked [B,H,W] tensor) */
   const B200AugSrc* src_table;

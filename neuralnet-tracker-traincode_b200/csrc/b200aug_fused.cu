@@ -29,16 +29,22 @@ namespace b200aug {
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 static_assert(NTHREADS == 256, "thread v owns photometric LUT entry v");
-constexpr int RMAX = 5;            // column rounds (of 32) per group: 160 output columns share one staged segment
+constexpr int RMAX = 4;            // column rounds (of 32) per group: 128 output columns share one staged segment
+constexpr int TAIL_COLS = 8;       // a last group of at most this many columns (129 = 128 + 1) goes through the per-pixel path
+                                   // instead of costing every canvas row a nearly empty round
 constexpr int KMAX = 6;            // widest INTER_AREA tap count the register path unrolls (scale factors up to ~5)
 constexpr int ROWBUF_SLACK = 16;   // the word-wise tap fetch may touch up to 11 bytes past the last tap
 constexpr int DT_CAP = 512;        // widest warp canvas with per-column delta tables in shared memory
-constexpr int DEFAULT_ROWBUF = 2560;  // per-warp staging bytes: a ring of up to RING_MAX crop rows in flight, or one
-                                      // staged warpAffine tile footprint (39 rows x 64 B)
-constexpr int RING_MAX = 8;
+constexpr int DEFAULT_ROWBUF = 3584;  // per-warp staging bytes: a ring of RING_D crop-row segments in flight (up to 850 B each:
+                                      // 160 output columns at scale factors up to ~5), or one staged warpAffine tile
+                                      // footprint (39 rows x 64 B)
+constexpr int RING_D = 4;          // canvas rows in flight per warp (cp.async commit groups)
 constexpr int ROWPROG_CAP = 96;    // canvas rows one warp can stream per band (its vertical-pass program, 8 B per row)
 constexpr int DEFAULT_CLUSTER = 2;  // CTAs sharing one sample
 constexpr int LAB_CAP = 1024;      // floats of label data staged in shared memory while the plan is being built
+
+// bytes of one ring slot for a row segment of `seg_bytes`: alignment shift (<= 15) + 16-byte granular copy + tap over-read
+__host__ __device__ __forceinline__ int ring_slot_bytes(int seg_bytes) { return (seg_bytes + 15 + 15 + ROWBUF_SLACK) & ~15; }
 
 enum SrcMode { SRC_CROP = 0, SRC_WARP = 1, SRC_PLAIN = 2 };
 enum RsMode { RS_COPY = 0, RS_AREA = 1, RS_AREA_INT = 2, RS_LINEAR = 3 };
@@ -93,7 +99,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ow, int oh, int cap) {
   L.off_dtab = o;
   o += (size_t)DT_CAP * sizeof(int2);
   L.off_bars = o;
-  o += (size_t)(NWARPS * RING_MAX + 2) * sizeof(uint64_t);  // ring barriers + the cluster exchange barrier
+  o += 2 * sizeof(uint64_t);  // the cluster exchange barrier
   L.off_lab = o;
   o += (size_t)LAB_CAP * sizeof(float);
   L.off_prog = o;
@@ -545,7 +551,8 @@ __device__ __forceinline__ int bilinear_q5(int p00, int p01, int p10, int p11, i
 __device__ int canvas_px(const Plan& P, int x, int y) {
   if (P.src_mode != SRC_WARP) {
     const int sx = P.x0 + x, sy = P.y0 + y;
-    return (sx >= 0 && sx < P.sw && sy >= 0 && sy < P.sh) ? (int)__ldg(P.src + (size_t)sy * P.pitch + sx) : 0;
+    // (coherent load: the source may be the scratch canvas written earlier in this kernel)
+    return (sx >= 0 && sx < P.sw && sy >= 0 && sy < P.sh) ? (int)P.src[(size_t)sy * P.pitch + sx] : 0;
   }
   const int X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[1], (double)y), P.mi[2]), 1024.0)) + 16;
   const int Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[4], (double)y), P.mi[5]), 1024.0)) + 16;
@@ -626,44 +633,6 @@ __device__ __forceinline__ int stage_crop_row(const Plan& P, int y, int lo, int 
     buf[i] = (row_in && sx >= 0 && sx < P.sw) ? P.src[(size_t)sy * P.pitch + sx] : (uint8_t)0;  // coherent load: the
   }                                                    // source may be the scratch canvas written earlier in this kernel
   return 0;
-}
-
-// Canvas row `y` of the warp, columns [lo, hi), into `buf`.  dtab[x] = (adelta, bdelta) of cv2's per-column tables.
-// Rows whose two end points map inside the source (all four taps valid; the map is monotone along the row) skip the
-// border predicates.
-__device__ __forceinline__ void stage_warp_row(const Plan& P, const int2* __restrict__ dtab, int y, int lo, int hi,
-                                               uint8_t* buf, int lane) {
-  const int X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[1], (double)y), P.mi[2]), 1024.0)) + 16;
-  const int Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[4], (double)y), P.mi[5]), 1024.0)) + 16;
-  const int2 da = dtab[lo], db = dtab[hi - 1];
-  const int ixa = (X0 + da.x) >> 10, ixb = (X0 + db.x) >> 10, iya = (Y0 + da.y) >> 10, iyb = (Y0 + db.y) >> 10;
-  const bool interior = min(ixa, ixb) >= 0 && max(ixa, ixb) + 1 < P.sw && min(iya, iyb) >= 0 && max(iya, iyb) + 1 < P.sh;
-  const int pitch = P.pitch;
-  const uint8_t* __restrict__ src = P.src;
-  if (interior) {
-#pragma unroll 4
-    for (int i = lane; i < hi - lo; i += 32) {
-      const int2 d = dtab[lo + i];
-      const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
-      const uint8_t* p = src + (X >> 5) + (Y >> 5) * pitch;
-      buf[i] = (uint8_t)bilinear_q5(__ldg(p), __ldg(p + 1), __ldg(p + pitch), __ldg(p + pitch + 1), X & 31, Y & 31);
-    }
-  } else {
-    const int sw = P.sw, sh = P.sh;
-    for (int i = lane; i < hi - lo; i += 32) {
-      const int2 d = dtab[lo + i];
-      const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
-      const int ix = X >> 5, iy = Y >> 5;
-      const bool r0 = (unsigned)iy < (unsigned)sh, r1 = (unsigned)(iy + 1) < (unsigned)sh;
-      const bool c0 = (unsigned)ix < (unsigned)sw, c1 = (unsigned)(ix + 1) < (unsigned)sw;
-      const uint8_t* p = src + (ptrdiff_t)iy * pitch + ix;
-      const int p00 = (r0 && c0) ? __ldg(p) : 0;
-      const int p01 = (r0 && c1) ? __ldg(p + 1) : 0;
-      const int p10 = (r1 && c0) ? __ldg(p + pitch) : 0;
-      const int p11 = (r1 && c1) ? __ldg(p + pitch + 1) : 0;
-      buf[i] = (uint8_t)bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ warpAffine, tile-staged
@@ -817,11 +786,13 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 // rows that feed it exactly once, in order.  Per canvas row: horizontal pass for the lane's columns (registers hold
 // the column taps), then the vertical accumulation in source-row order; a row shared by two output rows (fractional
 // boundary) is used for both.
-// Crop rows inside the frame stream through a per-warp ring of D slots: lane 0 keeps D bulk copies (16-byte aligned
-// supersets of the row segment) in flight, each completing on its slot's mbarrier.  Rows on the frame border are
-// staged synchronously (zero padded), rows outside the frame are zero, warp rows are computed into the staging row.
-template <int K, bool is_warp>
-__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int warp, int lane, int cr, int cl) {
+// Crop rows inside the frame stream through a per-warp ring of D slots (cp.async, 16 bytes per lane, a fixed number of
+// 16-byte vectors per row: the aligned superset of the row segment).  The band is walked in three phases so that the
+// steady state carries no row classification: rows above the frame (zeros) / the fetched rows / rows below the frame or
+// the frame's last row when its over-read would leave the image (staged synchronously, zero padded).
+// The canvas is always a crop here: rotated samples were turned into one by warp_canvas_to_scratch().
+template <int K>
+__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int ow_band, int warp, int lane, int cr, int cl) {
   const int rows_lo = (cr * oh) / cl, rows_n = ((cr + 1) * oh) / cl - rows_lo;  // this CTA's band of output rows
   const int dy_begin = rows_lo + (warp * rows_n) / NWARPS, dy_end = rows_lo + ((warp + 1) * rows_n) / NWARPS;
   if (dy_begin >= dy_end) return;
@@ -836,19 +807,17 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   T.a = reinterpret_cast<float*>(T.n + L.ntab);
   T.b = T.a + L.ntab;
   T.c = T.b + L.ntab;
-  uint8_t* const tile = smem + L.off_tile;
+  const uint32_t tile32 = smem_u32(smem + L.off_tile);
   uint8_t* const rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
-  const int2* const dtab = reinterpret_cast<const int2*>(smem + L.off_dtab);
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
 
   // plan fields used per row live in registers (the tile stores would otherwise force reloads from shared memory)
   const uint8_t* const src = P.src;
   const int pitch = P.pitch, x0 = P.x0, y0 = P.y0, sw = P.sw, sh = P.sh, cw = P.cw;
   const int fin = P.fin;
   const float inv_area = P.inv_area;
-  // canvas columns [cfl, cfh) lie inside the frame; taps outside read zeros (BORDER_CONSTANT / zero padding), which is
-  // the same as giving them weight +0 -- so only the in-frame part of a row is ever fetched
-  const int cfl = is_warp ? 0 : max(0, -x0), cfh = is_warp ? cw : min(cw, sw - x0);
+  // canvas columns [cfl, cfh) lie inside the frame; taps outside read zeros (zero padding), which is the same as giving
+  // them weight +0 -- so only the in-frame part of a row is ever fetched
+  const int cfl = max(0, -x0), cfh = min(cw, sw - x0);
   const uint32_t rowbuf32 = smem_u32(rowbuf);
 
   // ---- vertical-pass program of this warp's band: for canvas row R0 + i, prog[i] = (+-beta_a, beta_b):
@@ -878,10 +847,18 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   }
   __syncwarp();
 
-  for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
-    const int gcols = min(32 * RMAX, ow - g0);
+  for (int g0 = 0; g0 < ow_band; g0 += 32 * RMAX) {
+    const int gcols = min(32 * RMAX, ow_band - g0);
     const int glast = g0 + gcols - 1;
-    int xoff[RMAX], tcol[RMAX];
+    const int seg_lo = max(T.start[g0], cfl);
+    const int seg_hi = max(min(T.start[glast] + (T.n[glast] & 0xffff), cfh), seg_lo);
+    const int seg_bytes = seg_hi - seg_lo;
+    int xb[RMAX];        // first tap of the column, relative to the segment
+    // the lane's columns are g0 + lane + 32 j, j < nvalid; their pixels in the tile row being accumulated sit at
+    // trow32 + j * cstep (shared-memory address, flip / rot90 folded in)
+    const int nvalid = (gcols - lane + 31) >> 5;
+    uint32_t trow32 = tile32 + (uint32_t)(tm.o + (g0 + lane) * tm.sb + dy_begin * tm.sa);
+    int cstep = 32 * tm.sb;
     float w[RMAX][K];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
@@ -891,100 +868,128 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
       const int xnf = T.n[dxc], xn = xnf & 0xffff;
       const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
       const float xaf = T.a[dxc], xam = T.b[dxc], xal = T.c[dxc];
-      xoff[j] = T.start[dxc];
-      tcol[j] = valid ? tm.o + dx * tm.sb : -1;
+      const int xs = T.start[dxc];
+      xb[j] = xs - seg_lo;
 #pragma unroll
       for (int t = 0; t < K; ++t) {
-        const int col = xoff[j] + t;
+        const int col = xs + t;
         w[j][t] = (valid && t < xn && col >= cfl && col < cfh) ? area_alpha(t, xn, xhf, xhl, xaf, xam, xal) : 0.f;
       }
     }
-    const int seg_lo = max(T.start[g0], cfl);
-    const int seg_hi = max(min(T.start[glast] + (T.n[glast] & 0xffff), cfh), seg_lo);
-    const int seg_bytes = seg_hi - seg_lo;
-    const int slot_bytes = (seg_bytes + 15 + 15 + ROWBUF_SLACK) & ~15;
-    const int D = max(1, min(RING_MAX, (cap + ROWBUF_SLACK) / slot_bytes));
+    // ring geometry: every fetched row is copied as `nvec` 16-byte vectors starting at the 16-byte boundary at or below
+    // its first byte, so the copy ends less than 16 * nvec bytes after the segment's first byte
+    // (the caller checked that RING_D slots fit the warp's row buffer and that nvec <= 64)
+    const int slot_bytes = ring_slot_bytes(seg_bytes);
+    const int nvec = (seg_bytes + 30) >> 4;
+    constexpr int D = RING_D;
+    const int ring_bytes = D * slot_bytes;
 
     // rows [f_lo, f_hi] are fetched asynchronously
     int f_lo = INT_MAX, f_hi = INT_MIN;
-    if (!is_warp && seg_bytes > 0) {
-      const bool last_ok = x0 + seg_hi + 16 <= sw;  // the 16-byte-granular copy of the frame's last row stays inside it
+    if (seg_bytes > 0) {
+      const bool last_ok = x0 + seg_lo + 16 * nvec <= sw;  // the copy of the frame's last row stays inside that row
       f_lo = max(R0, -y0);
       f_hi = min(R1, (last_ok ? sh - 1 : sh - 2) - y0);
+      if (f_lo > f_hi) { f_lo = INT_MAX; f_hi = INT_MIN; }
     }
-    int trow = dy_begin * tm.sa;  // tile offset of the output row being accumulated
     float acc[RMAX];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) acc[j] = 0.f;
 
-    // ring state of row r: slot index, its shared address, the global address of the row's segment
-    int s = 0;
-    uint32_t slot32 = rowbuf32;
+    // ring state of row r: byte offset of its slot, the global address of the row's segment
+    int s_off = 0;
     uintptr_t ga = reinterpret_cast<uintptr_t>(src) + (ptrdiff_t)(y0 + R0) * pitch + (x0 + seg_lo);
+    uintptr_t gf = ga + (ptrdiff_t)D * pitch;  // segment of row r + D, the one fetched while row r is consumed
+    uint32_t dst_lane = rowbuf32 + 16u * (uint32_t)lane, rb32 = rowbuf32, lane16 = 16u * (uint32_t)lane;
+    int row_sa = tm.sa, slot_b = slot_bytes, ring_b = ring_bytes;
+    int my_vecs = (lane < nvec ? 1 : 0) + (lane + 32 < nvec ? 1 : 0);  // 16-byte vectors of a row this lane copies
+    // opaque to the optimiser: otherwise it rematerialises these from the kernel parameters inside the row loop
+    asm volatile("" : "+r"(dst_lane), "+r"(rb32), "+r"(trow32), "+r"(cstep), "+r"(row_sa));
+    asm volatile("" : "+r"(lane16), "+r"(slot_b), "+r"(ring_b), "+r"(my_vecs));
     // one commit group per row, in row order (an empty group for rows that are not fetched): when row r is consumed,
     // the groups of rows <= r + D - 1 have been committed, so "all but the D - 1 newest complete" means row r has landed
-    auto issue = [&](int slot, uintptr_t g, bool fetch) {  // whole warp: 16 bytes per lane
+    auto issue = [&](int soff, uintptr_t g, bool fetch) {  // whole warp: 16 bytes per lane
       if (fetch) {
-        const uint32_t shift = (uint32_t)(g & 15), nvec = (shift + (uint32_t)seg_bytes + 15u) >> 4;
-        const uint32_t dst = rowbuf32 + (uint32_t)(slot * slot_bytes);
-        for (uint32_t v = lane; v < nvec; v += 32)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * v), "l"(g - shift + 16u * v) : "memory");
+        const uintptr_t g16 = (g & ~uintptr_t(15)) + lane16;
+        const uint32_t d16 = dst_lane + (uint32_t)soff;
+        if (my_vecs > 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d16), "l"(g16) : "memory");
+        if (my_vecs > 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d16 + 512u), "l"(g16 + 512u) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    __syncwarp();
-    for (int i = 0; i < D; ++i) issue(i, ga + (ptrdiff_t)i * pitch, R0 + i >= f_lo && R0 + i <= f_hi);
-
-    for (int r = R0; r <= R1; ++r) {
-      float h[RMAX];
-      const int sy = y0 + r;
-      bool zero_row = false;
-      if (is_warp) {
-        __syncwarp();
-        stage_warp_row(P, dtab, r, seg_lo, seg_hi, rowbuf, lane);
-        __syncwarp();
-        hrow<K>(rowbuf32 - seg_lo, xoff, w, h);
-      } else if (is_warp) {  // (compile-time split: the branches below are the crop variant)
-      } else if (r >= f_lo && r <= f_hi) {
-        cp_async_wait_pending(D - 1);
-        __syncwarp();  // every lane's 16 bytes of the row are in
-        hrow<K>(slot32 + ((uint32_t)ga & 15u) - seg_lo, xoff, w, h);
-      } else if (sy < 0 || sy >= sh) {
-        zero_row = true;
-      } else {  // frame border: zero-padded row staged synchronously in the row's own (idle) slot
-        __syncwarp();
-        stage_crop_row(P, r, seg_lo, seg_hi, rowbuf + s * slot_bytes, lane);
-        __syncwarp();
-        hrow<K>(slot32 - seg_lo, xoff, w, h);
-      }
-      if (zero_row) {
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j) h[j] = 0.f;
-      }
-      // vertical pass (see the program above); a fresh sum starts from +0, and 0 + x is exact
-      const float2 pr = prog[r - R0];
+    // vertical pass (see the program above); a fresh sum starts from +0, and 0 + x is exact
+    const float2* pp = prog;
+    auto vertical = [&](const float (&h)[RMAX]) {
+      const float2 pr = *pp++;
       const float ba = fabsf(pr.x);
 #pragma unroll
       for (int j = 0; j < RMAX; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(ba, h[j]));
       if (pr.x < 0.f) {
+        if (fin == 0) {
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j) {
-          uint32_t q;
-          if (fin == 0) q = cvt_rni_sat_u8(acc[j]);
-          else if (fin == 1) q = (uint32_t)(((int)acc[j] + 2) >> 2);
-          else q = cvt_rni_sat_u8(__fmul_rn(acc[j], inv_area));
-          if (tcol[j] >= 0) tile[tcol[j] + trow] = (uint8_t)q;
-          acc[j] = __fmul_rn(pr.y, h[j]);
+          for (int j = 0; j < RMAX; ++j) {
+            const uint32_t q = cvt_rni_sat_u8(acc[j]);
+            if (j < nvalid) asm volatile("st.shared.u8 [%0], %1;" ::"r"(trow32 + (uint32_t)(j * cstep)), "r"(q) : "memory");
+            acc[j] = __fmul_rn(pr.y, h[j]);
+          }
+        } else {  // integer factors: (sum + 2) >> 2 for exact 2 x 2, rint(sum / area) otherwise
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) {
+            const uint32_t q = (fin == 1) ? (uint32_t)(((int)acc[j] + 2) >> 2) : cvt_rni_sat_u8(__fmul_rn(acc[j], inv_area));
+            if (j < nvalid) asm volatile("st.shared.u8 [%0], %1;" ::"r"(trow32 + (uint32_t)(j * cstep)), "r"(q) : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) acc[j] = __fmul_rn(pr.y, h[j]);
         }
-        trow += tm.sa;
+        trow32 += (uint32_t)row_sa;
       }
-      if (!is_warp) {
-        // the slot of row r is free again: refill it with row r + D
-        __syncwarp();
-        issue(s, ga + (ptrdiff_t)D * pitch, r + D >= f_lo && r + D <= f_hi);
-        ga += pitch;
-        if (++s == D) s = 0;
-        slot32 = rowbuf32 + (uint32_t)(s * slot_bytes);
+    };
+    auto advance = [&]() {
+      ga += pitch;
+      gf += pitch;
+      s_off += slot_b;
+      if (s_off == ring_b) s_off = 0;
+    };
+    __syncwarp();
+    for (int i = 0; i < D; ++i) issue(i * slot_bytes, ga + (ptrdiff_t)i * pitch, R0 + i >= f_lo && R0 + i <= f_hi);
+
+    int r = R0;
+#pragma unroll 1
+    for (int phase = 0; phase < 3; ++phase) {
+      if (phase == 1) {
+        // steady state: row r has been fetched into its slot
+#pragma unroll 1
+        for (; r <= f_hi; ++r) {
+          static_assert(RING_D == 4, "wait_group immediate");
+          asm volatile("cp.async.wait_group 3;" ::: "memory");
+          __syncwarp();  // every lane's 16 bytes of the row are in
+          float h[RMAX];
+          hrow<K>(rb32 + (uint32_t)s_off + ((uint32_t)ga & 15u), xb, w, h);
+          vertical(h);
+          __syncwarp();  // the slot of row r is free again: refill it with row r + D
+          issue(s_off, gf, r + D <= f_hi);
+          advance();
+        }
+      } else {
+        const int r_end = (phase == 0) ? min(R1, f_lo - 1) : R1;
+#pragma unroll 1
+        for (; r <= r_end; ++r) {
+          float h[RMAX];
+          const int sy = y0 + r;
+          if (sy < 0 || sy >= sh || seg_bytes <= 0) {  // above / below the frame
+#pragma unroll
+            for (int j = 0; j < RMAX; ++j) h[j] = 0.f;
+          } else {  // the frame's last row: zero-padded, staged synchronously in the row's own (idle) slot
+            __syncwarp();
+            stage_crop_row(P, r, seg_lo, seg_hi, rowbuf + s_off, lane);
+            __syncwarp();
+            hrow<K>(rb32 + (uint32_t)s_off, xb, w, h);
+          }
+          vertical(h);
+          __syncwarp();
+          issue(s_off, gf, r + D >= f_lo && r + D <= f_hi);
+          advance();
+        }
       }
     }
   }
@@ -1081,9 +1086,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   uint8_t* tile = smem + L.off_tile;
   uint8_t* rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
   int2* dtab = reinterpret_cast<int2*>(smem + L.off_dtab);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars) + warp * RING_MAX;
   float* lab = reinterpret_cast<float*>(smem + L.off_lab);
-  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.off_bars) + NWARPS * RING_MAX;  // cluster exchange barrier
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // cluster exchange barrier
 
   trace_mark(a, 0);
   if (a.trace_out && tid == 0) {
@@ -1091,9 +1095,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     a.trace_out[(size_t)blockIdx.x * 8 + 5] = smid;
   }
-  if (lane == 0) {
-    for (int s = 0; s < RING_MAX; ++s) mbar_init(&bars[s], 1);
-    if (warp == 0) mbar_init(xbar, 1);
+  if (tid == 0) {
+    mbar_init(xbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // ---- label data of this sample -> shared memory (overlaps the plan; labels do not depend on it) ----------
@@ -1263,8 +1266,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   trace_mark(a, 6);
   // ---- resample into the uint8 tile -----------------------------------------------------------------------
   const TileMap tm = make_tile_map(P, ow, oh);
-  bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) &&
-              (P.src_mode != SRC_WARP || use_dtab);
+  // columns [0, ow_band) are resampled by the warps' bands, a short last group by the per-pixel path
+  const int ow_tail = ow % (32 * RMAX);
+  const int ow_band = (ow_tail != 0 && ow_tail <= TAIL_COLS) ? ow - ow_tail : ow;
+  bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) && (P.src_mode != SRC_WARP) &&
+              ow_band > 0;
   if (fast) {
     // a warp's band of canvas rows must fit its vertical-pass program
     const int rows_per_warp = (rows_hi - rows_lo + NWARPS - 1) / NWARPS;
@@ -1273,21 +1279,24 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   }
   if (fast) {
     // every column group's canvas segment must fit the per-warp row buffer (only staged rows need it)
-    for (int g0 = 0; g0 < ow; g0 += 32 * RMAX) {
-      const int glast = min(g0 + 32 * RMAX, ow) - 1;
-      if (T.start[glast] + (T.n[glast] & 0xffff) - T.start[g0] + 48 > cap) fast = false;
+    for (int g0 = 0; g0 < ow_band; g0 += 32 * RMAX) {
+      const int glast = min(g0 + 32 * RMAX, ow_band) - 1;
+      const int seg = T.start[glast] + (T.n[glast] & 0xffff) - T.start[g0];
+      if (RING_D * ring_slot_bytes(seg) > cap + ROWBUF_SLACK || seg + 30 > 64 * 16) fast = false;
     }
   }
   if (fast) {
     const int kx = P.kx;
-#define B200AUG_BAND(KK)                                                                                   \
-  (P.src_mode == SRC_WARP ? area_band<KK, true>(tm, cap, ow, oh, warp, lane, cr, cl)                      \
-                          : area_band<KK, false>(tm, cap, ow, oh, warp, lane, cr, cl))
+#define B200AUG_BAND(KK) area_band<KK>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl)
     if (kx <= 3) B200AUG_BAND(3);
     else if (kx == 4) B200AUG_BAND(4);
-    else if (kx == 5) B200AUG_BAND(5);
     else B200AUG_BAND(6);
 #undef B200AUG_BAND
+    const int tw = ow - ow_band;
+    for (int p = tid; p < (rows_hi - rows_lo) * tw; p += NTHREADS) {
+      const int dy = rows_lo + p / tw, dx = ow_band + p % tw;
+      tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
+    }
   } else if (P.status == B200AUG_S_OK) {
     // per-pixel path: integer-factor area, linear up-scaling, plain copy, very wide taps / canvases
     for (int p = rows_lo * ow + tid; p < rows_hi * ow; p += NTHREADS) {
