@@ -145,8 +145,9 @@ typedef struct B200AugFusedArgs {
   uint8_t* image_u8_out;        /* [B,1,oh,ow] when F_NORMALIZE is not set */
   float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
   int32_t* status_out;          /* [B] B200AUG_S_* */
-  uint64_t* trace_out;          /* [B*cluster_size,8] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / tables
-                                   built / resample done / end, then %smid, warp stage done, 0 */
+  uint64_t* trace_out;          /* [B*cluster_size,16] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / cluster
+                                   synchronised / resample done / end, then %smid, warp stage done, tables+columns built, resize tables
+                                   built, labels done, photometric LUT built; the rest 0 */
   /* optional launch order: order[i] = sample processed by the i-th cluster of the grid (a permutation of 0..B-1).  The
    * CTAs are dispatched in grid order, so listing the expensive samples (rotated, blurred, noisy) first lets the cheap
    * ones fill the tail.  NULL = identity. */

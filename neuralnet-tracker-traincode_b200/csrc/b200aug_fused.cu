@@ -157,7 +157,7 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
 }
 
 __device__ __forceinline__ void trace_mark(const B200AugFusedArgs& a, int slot) {
-  if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)blockIdx.x * 8 + slot] = globaltimer_ns();
+  if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)blockIdx.x * 16 + slot] = globaltimer_ns();
 }
 
 // ---- thread-block clusters: the CTAs of a cluster share one sample (each resamples a band of rows and stores the
@@ -436,36 +436,50 @@ __device__ void run_item_chain(const Plan& P, uint32_t flags, int category, floa
   if (flags & B200AUG_F_NORMALIZE) transform_item(P.t3, category, v, dim);
 }
 
-// `staged`: the transformable fields of this sample, packed in field order in shared memory (or NULL)
-__device__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b, const float* staged) {
+// `staged`: the transformable fields of this sample, packed in field order in shared memory (or NULL).
+// All items of all transformable fields form one flat list that the threads of the CTA share (one pass for the pose
+// pipeline's 68 + 1 + 1 + 1 items): the fields are not walked one after the other.
+__device__ __noinline__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b, const float* staged) {
   // an odd number of mirroring transforms permutes the left/right landmarks
   const bool flip_parity = (((a.flags & B200AUG_F_FOCUS) && P.t1.det < 0.f) + (P.has_t2 && P.t2.det < 0.f)) & 1;
-  int off = 0;
+  int total = 0;
   for (int f = 0; f < a.n_fields; ++f) {
     const B200AugField& F = a.fields[f];
     if (!F.out || !F.in) continue;
-    const int dim = F.dim, cnt = F.count;
-    const float* in = F.in + (size_t)b * cnt * dim;
-    float* out = F.out + (size_t)b * cnt * dim;
-    if (F.category == B200AUG_CAT_GENERAL || dim > 4) {
+    if (F.category == B200AUG_CAT_GENERAL || F.dim > 4) {
+      const float* in = F.in + (size_t)b * F.count * F.dim;
+      float* out = F.out + (size_t)b * F.count * F.dim;
       if (in != out)
-        for (int i = threadIdx.x; i < cnt * dim; i += NTHREADS) out[i] = in[i];
+        for (int i = threadIdx.x; i < F.count * F.dim; i += NTHREADS) out[i] = in[i];
       continue;
     }
-    if (staged) {
-      in = staged + off;
-      off += cnt * dim;
+    total += F.count;
+  }
+  for (int t = threadIdx.x; t < total; t += NTHREADS) {
+    // locate item t: field f, index i, offset of the field in the staged copy
+    int f = 0, i = t, off = 0;
+    for (; f < a.n_fields; ++f) {
+      const B200AugField& F = a.fields[f];
+      if (!F.out || !F.in || F.category == B200AUG_CAT_GENERAL || F.dim > 4) continue;
+      if (i < F.count) break;
+      i -= F.count;
+      off += F.count * F.dim;
     }
+    const B200AugField& F = a.fields[f];
     const bool is_roi_from_lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && f == a.roi_field;
-    if (is_roi_from_lm) continue;  // written by warp 0 in the prologue
-    for (int i = threadIdx.x; i < cnt; i += NTHREADS) {
-      int si = i;
-      if (F.category == B200AUG_CAT_POINTS && cnt == 68 && flip_parity) si = flip_map68(i);
-      float v[4];
-      for (int k = 0; k < dim; ++k) v[k] = in[si * dim + k];
-      run_item_chain(P, a.flags, F.category, v, dim);
-      for (int k = 0; k < dim; ++k) out[i * dim + k] = v[k];
-    }
+    if (is_roi_from_lm) continue;  // written by warp 2 in the prologue
+    const int dim = F.dim, cnt = F.count, cat = F.category;
+    const float* in = staged ? staged + off : F.in + (size_t)b * cnt * dim;
+    float* out = F.out + (size_t)b * cnt * dim;
+    const int si = (cat == B200AUG_CAT_POINTS && cnt == 68 && flip_parity) ? flip_map68(i) : i;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < dim) v[k] = in[si * dim + k];
+    run_item_chain(P, a.flags, cat, v, dim);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < dim) out[i * dim + k] = v[k];
   }
 }
 
@@ -581,7 +595,7 @@ __device__ __forceinline__ float area_alpha(int t, int n, bool hf, bool hl, floa
 
 // One output pixel of the resize, scalar, for every resampler (the fallback path and the reference semantics of the
 // fast path): cv2.resize INTER_AREA (general + integer factor), INTER_LINEAR, or a plain copy.
-__device__ uint8_t scalar_out_px(const Plan& P, const Tabs& T, int ow, int dx, int dy) {
+__device__ __noinline__ uint8_t scalar_out_px(const Plan& P, const Tabs& T, int ow, int dx, int dy) {
   switch (P.rs_mode) {
     case RS_AREA: {
       const int xs = T.start[dx], xnf = T.n[dx], xn = xnf & 0xffff;
@@ -998,7 +1012,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
 // ------------------------------------------------------------------------------------------------ photometric helpers
 
 // pointwise stage-1 ops [from, to) of this sample's op list applied to x (oracle/photometric.py)
-__device__ float apply_point_ops(const Plan& P, float x, int from, int to, const float* eq_lut) {
+__device__ __noinline__ float apply_point_ops(const Plan& P, float x, int from, int to, const float* eq_lut) {
   for (int k = from; k < to; ++k) {
     switch (P.ops[k]) {
       case B200AUG_OP_EQUALIZE: {
@@ -1036,7 +1050,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 // value of pixel p after the LUT prefix and the 5x5 blur: input to the post-blur ops
-__device__ float blurred_value(const uint8_t* tile, const float* lut, int ow, int oh, int p) {
+__device__ __noinline__ float blurred_value(const uint8_t* tile, const float* lut, int ow, int oh, int p) {
   const int y = p / ow, x = p - y * ow;
   // gaussian_blur2d(5, sigma 1.5), reflect border, horizontal pass then vertical pass (oracle/photometric.py)
   // float32(exp(-t^2/(2 sigma^2))) / float32 sum, identical to oracle/photometric.py:gaussian_kernel1d
@@ -1093,7 +1107,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   if (a.trace_out && tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    a.trace_out[(size_t)blockIdx.x * 8 + 5] = smid;
+    a.trace_out[(size_t)blockIdx.x * 16 + 5] = smid;
   }
   if (tid == 0) {
     mbar_init(xbar, 1);
@@ -1113,9 +1127,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       if (!(F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4)) continue;
       const int n = F.count * F.dim;
       const float* src = F.in + (size_t)b * n;
-      for (int i = tid; i < n; i += NTHREADS) lab[off + i] = src[i];
+      for (int i = tid; i < n; i += NTHREADS)  // asynchronous: the loads overlap the plan instead of stalling in front of it
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(lab + off + i)), "l"(src + i) : "memory");
       off += n;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // ---- prologue: the plan, one branch per warp (see plan_core) --------------------------------------------
   {
@@ -1184,6 +1200,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       default: break;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the staged labels
   __syncthreads();
 
   trace_mark(a, 1);
@@ -1200,15 +1217,20 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(xbar)), "r"(rx_bytes) : "memory");
   }
   if (tid == 0 && a.status_out) a.status_out[b] = P.status;
-  if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
-
+  // The labels only need the plan; they are transformed once the CTAs of the cluster no longer wait for each other (after the
+  // tile exchange), so that rank 0 does not hold its partner up in front of the resampling.
   const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
-  if (!want_image) return;
+  if (!want_image) {
+    if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
+    return;
+  }
 
   // ---- resize tables, warp column tables ------------------------------------------------------------------
   const int rs = P.rs_mode;
   if (rs == RS_AREA || rs == RS_LINEAR || rs == RS_AREA_INT) {
-    for (int i = tid; i < ow + oh; i += NTHREADS) {
+    // two independent entries per thread and iteration: 129 + 129 entries on 256 threads would otherwise pay a second,
+    // nearly empty, round of double-precision latency
+    auto tab_entry = [&](int i) {
       const bool is_x = i < ow;
       const int d = is_x ? i : i - ow;
       const double sc = is_x ? P.scale_x : P.scale_y;
@@ -1228,8 +1250,29 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
         linear_tab_entry(d, sc, ss, is_x, i0, i1, w0, w1);
         T.start[i] = i0; T.n[i] = i1; T.a[i] = __int_as_float(w0); T.b[i] = __int_as_float(w1);
       }
+    };
+    const int ntab = ow + oh;
+    if (rs == RS_AREA) {
+      for (int i = tid; i < ntab; i += 2 * NTHREADS) {
+        const int i2 = i + NTHREADS;
+        const bool two = i2 < ntab;
+        const int j = two ? i2 : i;  // (a lone entry is simply computed twice)
+        const bool x1 = i < ow, x2 = j < ow;
+        int st1, nf1, st2, nf2; float af1, am1, al1, af2, am2, al2;
+        area_tab_entry(x1 ? i : i - ow, x1 ? P.scale_x : P.scale_y, x1 ? P.cw : P.ch, st1, nf1, af1, am1, al1);
+        area_tab_entry(x2 ? j : j - ow, x2 ? P.scale_x : P.scale_y, x2 ? P.cw : P.ch, st2, nf2, af2, am2, al2);
+        T.start[i] = st1; T.n[i] = nf1; T.a[i] = af1; T.b[i] = am1; T.c[i] = al1;
+        T.start[j] = st2; T.n[j] = nf2; T.a[j] = af2; T.b[j] = am2; T.c[j] = al2;
+        int kmax = x1 ? (nf1 & 0xffff) : 0;
+        if (x2) kmax = max(kmax, nf2 & 0xffff);
+        kmax = __reduce_max_sync(__activemask(), kmax);
+        if (lane == 0 && kmax) atomicMax(&P.kx, kmax);
+      }
+    } else {
+      for (int i = tid; i < ntab; i += NTHREADS) tab_entry(i);
     }
   }
+  trace_mark(a, 8);
   const bool use_dtab = (P.src_mode == SRC_WARP) && (P.cw <= DT_CAP);
   if (use_dtab) {
     for (int x = tid; x < P.cw; x += NTHREADS)
@@ -1340,6 +1383,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   }
   cluster_sync(cl);  // every CTA's tile now holds the whole crop; no distributed-shared-memory access after this point
   trace_mark(a, 3);
+  if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
+  trace_mark(a, 9);
 
   // ---- uint8 output (geometric stages only) --------------------------------------------------------------
   if (!(a.flags & B200AUG_F_NORMALIZE)) {
@@ -1427,6 +1472,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     __syncthreads();
   }
 
+  trace_mark(a, 10);
   // ---- output pass ----------------------------------------------------------------------------------------
   float* out = a.image_f32_out + (size_t)b * npix;
   const int Q = (npix + 3) >> 2;

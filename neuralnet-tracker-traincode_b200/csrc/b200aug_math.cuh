@@ -83,7 +83,7 @@ struct AffDerived {  // per-transform scalars shared by all items of a sample
   float det, sqrt_abs_det, scales, detsign, qk, qw;
 };
 
-__device__ __forceinline__ AffDerived aff_derive(const Aff& m) {
+__device__ __noinline__ AffDerived aff_derive(const Aff& m) {
   AffDerived d;
   d.m = m;
   d.det = aff_det(m);

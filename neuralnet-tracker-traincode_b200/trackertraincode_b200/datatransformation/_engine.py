@@ -363,7 +363,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         args.status_out = status.data_ptr()
     trace = None
     if want_trace:  # per-CTA timeline (profiling aid, see include/b200aug.h: trace_out)
-        trace = torch.zeros((B * (cluster_size or 2), 8), dtype=torch.int64, device=device)
+        trace = torch.zeros((B * (cluster_size or 2), 16), dtype=torch.int64, device=device)
         args.trace_out = trace.data_ptr()
 
     # ---- assemble the result (tensors are written when the call is launched)

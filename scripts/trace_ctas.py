@@ -40,12 +40,16 @@ t0 = t[:, 0].min()
 start, plan, tabs, res, end, smid = (t[:, i] - (t0 if i < 5 else 0) for i in range(6))
 print(f"kernel span {(end.max()) / 1e3:.1f} us; CTA duration us: mean {np.mean(end - start) / 1e3:.1f} median {np.median(end - start) / 1e3:.1f} "
       f"p95 {np.percentile(end - start, 95) / 1e3:.1f} max {(end - start).max() / 1e3:.1f}")
-rot = np.repeat(gp.angles != 0, CL)
-blur = np.repeat(pp.apply[:, 5] & (5 in list(pp.order)), CL)
-eq = np.repeat(pp.apply[:, 0] & (0 in list(pp.order)), CL)
-noise = np.repeat(pp.noise_apply.any(1), CL)
+_ord = E.launch_order(bench.BATCH, geo, photo)
+samp = _ord.numpy().astype(np.int64) if _ord is not None else np.arange(bench.BATCH)  # cluster i of the grid -> sample
+rot = np.repeat((gp.angles != 0)[samp], CL)
+blur = np.repeat((pp.apply[:, 5] & (5 in list(pp.order)))[samp].astype(bool), CL)
+eq = np.repeat((pp.apply[:, 0] & (0 in list(pp.order)))[samp].astype(bool), CL)
+noise = np.repeat(pp.noise_apply.any(1)[samp], CL)
 warp_stage = t[:, 6] - t0 - tabs
-ph = {"plan": plan - start, "lab+tab": t[:, 7] - t0 - plan, "csync": tabs - (t[:, 7] - t0), "warp": warp_stage, "resample": res - tabs, "photo+output": end - res, "total": end - start}
+m6, m7, m8, m9, m10 = (t[:, i] - t0 for i in (6, 7, 8, 9, 10))
+ph = {"plan": plan - start, "tab": m8 - plan, "dtab..": m7 - m8, "csync": tabs - m7, "warp": m6 - tabs, "area+xchg": res - m6, "labels": m9 - res,
+      "lut": np.where(m10 > 0, m10 - m9, 0), "output": np.where(m10 > 0, end - m10, end - m9), "total": end - start}
 for name, m in (("all", np.ones_like(rot)), ("unrotated", ~rot), ("rotated", rot), ("blur", blur), ("equalize", eq), ("noise", noise),
                 ("plain(no rot/photo)", ~rot & ~blur & ~eq & ~noise)):
     if m.sum():
@@ -56,10 +60,10 @@ for s, a, e in zip(smid, start, end):
     busy[s] = max(busy[s], e)
 sys.stdout.flush()
 print(f"per-SM last-CTA end (us): min {busy.min() / 1e3:.1f} median {np.median(busy) / 1e3:.1f} max {busy.max() / 1e3:.1f}; SMs used {len(np.unique(smid))}")
-vr = np.repeat(call.result.view_roi.cpu().numpy(), CL, axis=0)
+vr = np.repeat(call.result.view_roi.cpu().numpy()[samp], CL, axis=0)
 dur = end - start
 for i in np.argsort(-dur)[:8]:
-    print(f"slow cta {i} (sample {i // CL}): total {dur[i] / 1e3:.1f} us resample {(res - tabs)[i] / 1e3:.1f} view_roi {vr[i].tolist()} size {(vr[i, 2] - vr[i, 0], vr[i, 3] - vr[i, 1])} "
+    print(f"slow cta {i} (sample {samp[i // CL]}): total {dur[i] / 1e3:.1f} us area {(res - (t[:, 6] - t0))[i] / 1e3:.1f} view_roi {vr[i].tolist()} size {(vr[i, 2] - vr[i, 0], vr[i, 3] - vr[i, 1])} "
           f"rot {bool(rot[i])} blur {bool(blur[i])} eq {bool(eq[i])} noise {bool(noise[i])} sm {smid[i]} start {start[i] / 1e3:.1f}")
 if len(sys.argv) > 1:
     np.savez(sys.argv[1], trace=t, rot=rot, blur=blur, eq=eq, noise=noise)
