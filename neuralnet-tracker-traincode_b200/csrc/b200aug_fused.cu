@@ -687,10 +687,15 @@ __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ d
     const int bx0 = min(min(ix0, ix1), min(ix2, ix3)), bx1 = max(max(ix0, ix1), max(ix2, ix3)) + 1;
     const int by0 = min(min(iy0, iy1), min(iy2, iy3)), by1 = max(max(iy0, iy1), max(iy2, iy3)) + 1;
     const int nrows = by1 - by0 + 1;
+    // Staged layout: box row r is copied as four 16-byte chunks starting at the aligned address at or below its first byte,
+    // to shared-memory offset S_r = 64 r + 16 ((c0 + r pm) >> 4), c0 = alignment shift of row 0, pm = pitch mod 16.  The byte
+    // of box row r, box column x then sits at c0 + r (64 + pm) + x: linear in r, so the gather needs no per-row shift.
+    const uintptr_t gbase = reinterpret_cast<uintptr_t>(src) + (size_t)by0 * pitch + bx0;  // top-left of the box
+    const int c0 = (int)(gbase & 15);
+    const int rstride = WT_STRIDE + pm;
     // staged: inside the frame (and not on its last row: the 16-byte chunks may run past a row's end), small enough
     const bool staged = bx0 >= 0 && bx1 < sw && by0 >= 0 && by1 < sh - 1 && nrows <= WT_ROWS && (bx1 - bx0 + 1) + 15 <= WT_STRIDE &&
-                        nrows * WT_STRIDE <= stage_bytes;
-    const uintptr_t gbase = reinterpret_cast<uintptr_t>(src) + (size_t)by0 * pitch + bx0;  // top-left of the box
+                        (nrows - 1) * WT_STRIDE + 16 * ((c0 + (nrows - 1) * pm) >> 4) + WT_STRIDE <= stage_bytes;
     __syncwarp();
     if (staged) {
       // item = (row, 16-byte chunk); all loads first, then the stores
@@ -706,29 +711,28 @@ __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ d
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int item = lane + 32 * i, row = item >> 2, k = item & 3;
-        if (row < nrows) *reinterpret_cast<uint4*>(stage + row * WT_STRIDE + 16 * k) = v[i];
+        if (row < nrows) *reinterpret_cast<uint4*>(stage + row * WT_STRIDE + 16 * ((c0 + row * pm) >> 4) + 16 * k) = v[i];
       }
       __syncwarp();
-      const int c0 = (int)(gbase & 15);  // alignment shift of box row r: (c0 + r * pm) & 15
       int X0l, Y0l;                      // lane yy holds the row origin of tile row yy
       row_origin(y_lo + min(lane, th - 1), X0l, Y0l);
       const int2 d = dtab[x_lo + min(lane, tw - 1)];
+      // shared-memory address of source pixel (iy, ix) = tap0 + iy * rstride + ix
+      const uint32_t tap0 = stage32 + (uint32_t)(c0 - bx0 - by0 * rstride);
       uint8_t* out = scratch + (size_t)y_lo * spitch + x_lo + lane;
+      const bool act = lane < tw;  // (idle lanes repeat the last column: their addresses stay valid)
 #pragma unroll 4
       for (int yy = 0; yy < th; ++yy) {
-        const int X0 = __shfl_sync(0xffffffffu, X0l, yy), Y0 = __shfl_sync(0xffffffffu, Y0l, yy);
-        if (lane < tw) {
-          const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
-          const int ixr = (X >> 5) - bx0, iyr = (Y >> 5) - by0;
-          const int s0 = (c0 + iyr * pm) & 15, s1 = (s0 + pm) & 15;
-          const uint32_t a0 = stage32 + (uint32_t)(iyr * WT_STRIDE + s0 + ixr), a1 = stage32 + (uint32_t)((iyr + 1) * WT_STRIDE + s1 + ixr);
-          uint32_t p00, p01, p10, p11;
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a0) : "memory");
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p01) : "r"(a0 + 1) : "memory");
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a1) : "memory");
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p11) : "r"(a1 + 1) : "memory");
-          out[(size_t)yy * spitch] = (uint8_t)bilinear_q5((int)p00, (int)p01, (int)p10, (int)p11, X & 31, Y & 31);
-        }
+        const int sx = __shfl_sync(0xffffffffu, X0l, yy) + d.x, sy = __shfl_sync(0xffffffffu, Y0l, yy) + d.y;  // 1/1024 px
+        const uint32_t a0 = tap0 + (uint32_t)((sy >> 10) * rstride + (sx >> 10)), a1 = a0 + (uint32_t)rstride;
+        uint32_t p00, p01, p10, p11;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a0) : "memory");
+        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(a0) : "memory");
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a1) : "memory");
+        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p11) : "r"(a1) : "memory");
+        const int q = bilinear_q5((int)p00, (int)p01, (int)p10, (int)p11, (sx >> 5) & 31, (sy >> 5) & 31);
+        if (act) *out = (uint8_t)q;
+        out += spitch;
       }
     } else if (lane < tw) {
       const int2 d = dtab[x_lo + lane];
@@ -1336,9 +1340,40 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     else B200AUG_BAND(6);
 #undef B200AUG_BAND
     const int tw = ow - ow_band;
-    for (int p = tid; p < (rows_hi - rows_lo) * tw; p += NTHREADS) {
-      const int dy = rows_lo + p / tw, dx = ow_band + p % tw;
-      tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
+    if (tw > 0 && rs == RS_AREA) {
+      // the tail column(s) of a general-factor INTER_AREA crop: scalar_out_px() specialised (plan fields in registers, crop
+      // source only), one thread per pixel
+      const uint8_t* const src = P.src;
+      const int pitch = P.pitch, sw = P.sw, sh = P.sh, x0 = P.x0, y0 = P.y0;
+      for (int p = tid; p < (rows_hi - rows_lo) * tw; p += NTHREADS) {
+        const int dy = rows_lo + p / tw, dx = ow_band + p % tw;
+        const int xs = T.start[dx], xnf = T.n[dx], xn = xnf & 0xffff;
+        const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
+        const float xaf = T.a[dx], xam = T.b[dx], xal = T.c[dx];
+        const int ys = T.start[ow + dy], ynf = T.n[ow + dy], yn = ynf & 0xffff;
+        const bool yhf = ynf & (1 << 30), yhl = ynf & (1u << 31);
+        const float yaf = T.a[ow + dy], yam = T.b[ow + dy], yal = T.c[ow + dy];
+        float acc = 0.f;
+        for (int k = 0; k < yn; ++k) {
+          const int sy = y0 + ys + k;
+          const bool row_in = (unsigned)sy < (unsigned)sh;
+          const uint8_t* row = src + (ptrdiff_t)sy * pitch + (x0 + xs);
+          float h = 0.f;
+          for (int t = 0; t < xn; ++t) {
+            const bool in = row_in && (unsigned)(x0 + xs + t) < (unsigned)sw;
+            const float px = in ? (float)row[t] : 0.f;  // (coherent load: the source may be the scratch canvas)
+            h = __fadd_rn(h, __fmul_rn(px, area_alpha(t, xn, xhf, xhl, xaf, xam, xal)));
+          }
+          const float beta = area_alpha(k, yn, yhf, yhl, yaf, yam, yal);
+          acc = (k == 0) ? __fmul_rn(beta, h) : __fadd_rn(acc, __fmul_rn(beta, h));
+        }
+        tile[tm.o + dy * tm.sa + dx * tm.sb] = sat_u8_rint(acc);
+      }
+    } else {
+      for (int p = tid; p < (rows_hi - rows_lo) * tw; p += NTHREADS) {
+        const int dy = rows_lo + p / tw, dx = ow_band + p % tw;
+        tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
+      }
     }
   } else if (P.status == B200AUG_S_OK) {
     // per-pixel path: integer-factor area, linear up-scaling, plain copy, very wide taps / canvases
@@ -1491,6 +1526,48 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   const uint64_t sid = a.photo.sample_offset + (uint64_t)b;
   const uint2 key = make_uint2((uint32_t)a.photo.seed, (uint32_t)(a.photo.seed >> 32));
   const bool blur = P.blur_pos >= 0;
+  // Blur: separable, strip by strip.  This CTA's pixels are the four ranges [g_lo, g_hi) + i Q; for each range the
+  // horizontal pass of its rows (+ 2 halo rows either side, reflect border) goes into the warps' idle row buffers as float32,
+  // then the vertical pass and the ops behind the blur produce the pre-noise value, parked in the output buffer itself.
+  float* const hb = reinterpret_cast<float*>(smem + L.off_rowbuf);
+  const int hb_rows = (int)(((size_t)NWARPS * (cap + ROWBUF_SLACK)) / (sizeof(float) * (size_t)ow));
+  const bool blur_strips = blur && hb_rows >= 6;
+  if (blur_strips) {
+    // float32(exp(-t^2/(2 sigma^2))) / float32 sum, identical to oracle/photometric.py:gaussian_kernel1d
+    const float g0 = 0x1.ebd752p-4f, g1 = 0x1.defcdep-3f, g2 = 0x1.2b1778p-2f;
+    const int strip = hb_rows - 4;
+    for (int i = 0; i < 4; ++i) {
+      const int p_lo = g_lo + i * Q, p_hi = min(g_hi + i * Q, npix);
+      if (p_lo >= p_hi) continue;
+      const int y_last = (p_hi - 1) / ow;
+      for (int ry0 = p_lo / ow; ry0 <= y_last; ry0 += strip) {
+        const int ry1 = min(ry0 + strip - 1, y_last), nr = ry1 - ry0 + 5;
+        __syncthreads();  // the previous strip's vertical pass is done with hb
+        for (int v = tid; v < nr * ow; v += NTHREADS) {
+          const int rr = v / ow, x = v - rr * ow;
+          const uint8_t* row = tile + reflect_idx(ry0 - 2 + rr, oh) * ow;
+          float t = __fmul_rn(g0, lut[row[reflect_idx(x - 2, ow)]]);
+          t = __fadd_rn(t, __fmul_rn(g1, lut[row[reflect_idx(x - 1, ow)]]));
+          t = __fadd_rn(t, __fmul_rn(g2, lut[row[x]]));
+          t = __fadd_rn(t, __fmul_rn(g1, lut[row[reflect_idx(x + 1, ow)]]));
+          t = __fadd_rn(t, __fmul_rn(g0, lut[row[reflect_idx(x + 2, ow)]]));
+          hb[v] = t;
+        }
+        __syncthreads();
+        const int q_lo = max(p_lo, ry0 * ow), q_hi = min(p_hi, (ry1 + 1) * ow);
+        for (int p = q_lo + tid; p < q_hi; p += NTHREADS) {
+          const float* c = hb + (p - ry0 * ow);  // horizontal-pass value of the pixel two rows up
+          float acc = __fmul_rn(g0, c[0]);
+          acc = __fadd_rn(acc, __fmul_rn(g1, c[ow]));
+          acc = __fadd_rn(acc, __fmul_rn(g2, c[2 * ow]));
+          acc = __fadd_rn(acc, __fmul_rn(g1, c[3 * ow]));
+          acc = __fadd_rn(acc, __fmul_rn(g0, c[4 * ow]));
+          out[p] = apply_point_ops(P, acc, P.blur_pos + 1, P.n_ops, eq_lut);
+        }
+      }
+    }
+    __syncthreads();  // the parked values are read back by other threads of this CTA
+  }
   for (int g = g_lo + tid; g < g_hi; g += NTHREADS) {
     float x[4];
 #pragma unroll
@@ -1498,7 +1575,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       const int p = g + i * Q;
       float v = 0.f;
       if (p < npix) {
-        if (blur) v = apply_point_ops(P, blurred_value(tile, lut, ow, oh, p), P.blur_pos + 1, P.n_ops, eq_lut);
+        if (blur_strips) v = out[p];
+        else if (blur) v = apply_point_ops(P, blurred_value(tile, lut, ow, oh, p), P.blur_pos + 1, P.n_ops, eq_lut);
         else v = lut[tile[p]];
       }
       x[i] = v;
