@@ -83,6 +83,14 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise N.NativeError(f"{what} must live on a CUDA device (got {t.device}); this path has no CPU implementation")
 
 
+def _require_device_visible(t: torch.Tensor, what: str):
+    """Source frames may also stay in PINNED host memory: under unified addressing the kernel reads page-locked host
+    memory through the same pointer (zero copy), so only the bytes inside the view boxes ever cross PCIe."""
+    if not (t.is_cuda or t.is_pinned()):
+        raise N.NativeError(f"{what} must live on a CUDA device or in pinned host memory (got pageable {t.device} memory); "
+                            "this path has no CPU implementation")
+
+
 def _dev(t, device, dtype) -> torch.Tensor:
     t = torch.as_tensor(t)
     if t.dtype != dtype:
@@ -114,7 +122,7 @@ class _ImageSource:
             tab = np.zeros((len(imgs), 6), dtype=np.int32)
             ptrs = tab[:, :2].view(np.int64)
             for i, im in enumerate(imgs):
-                _require_cuda(im, "image")
+                _require_device_visible(im, "image")
                 ptrs[i, 0] = im.data_ptr()
                 tab[i, 2], tab[i, 3], tab[i, 4] = im.shape[1], im.shape[0], im.stride(0)
             self.keep += imgs
@@ -123,7 +131,7 @@ class _ImageSource:
             self.wh = None
             return
         v = value if batched else value[None]
-        _require_cuda(v, "image")
+        _require_device_visible(v, "image")
         if v.dtype != torch.uint8:
             raise TypeError(f"image must be uint8, got {v.dtype}")
         if v.dim() == 4:
@@ -234,7 +242,14 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     batched = meta.prefixshape != ()
     (B,) = meta.prefixshape if batched else (1,)
     ow, oh = (out_size, out_size) if isinstance(out_size, int) else tuple(out_size)
-    device = batch.device
+    # the device of the label fields decides (the source frames may be pinned host memory, read by the kernel in place)
+    device = None
+    for k, v in batch.items():
+        if isinstance(v, torch.Tensor) and (v.is_cuda or as_category(meta.categories.get(k)) not in imagelike_categories):
+            device = v.device
+            break
+    if device is None:
+        device = batch.device
     if device.type != "cuda":
         raise N.NativeError(f"batch lives on {device}; the B200 path needs CUDA tensors (there is no CPU fallback)")
 

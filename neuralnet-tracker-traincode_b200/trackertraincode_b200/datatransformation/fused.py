@@ -62,7 +62,7 @@ def draw_photo_params(B: int, seed: int, sample_offset: int) -> E.PhotoParams:
 class FusedPoseAugmentation:
     def __init__(self, inputsize: int = 129, rotation_aug_angle: float = 30.0, roi_override: str = "original",
                  enable_image_aug: bool = True, train: bool = True, p_rot: float = 0.01, device="cuda",
-                 seed: int = 0, rowbuf_capacity: int = 0):
+                 seed: int = 0, rowbuf_capacity: int = 0, zero_copy_frames: bool = False):
         if roi_override not in ("original", "landmarks"):
             raise N.NativeError("roi_override='extent_to_forehead' needs the BFM face model and is not on the B200 path")
         ext = {"original": 1.1, "landmarks": 1.2}[roi_override]  # pipelines.py:334
@@ -82,6 +82,7 @@ class FusedPoseAugmentation:
         self.seed = seed
         self.samples_seen = 0
         self.rowbuf_capacity = rowbuf_capacity
+        self.zero_copy_frames = zero_copy_frames
 
     def draw(self, B: int) -> AugmentationDraws:
         p = self.sampler((B,))
@@ -93,12 +94,38 @@ class FusedPoseAugmentation:
         photo = draw_photo_params(B, self.seed, self.samples_seen) if self.enable_image_aug else None
         return AugmentationDraws(geo, do_flip, rot_dir, photo)
 
+    def _to_device(self, batch: Batch) -> Batch:
+        """Batch.to(device) (pipelines.py:508) -- except that source frames in PINNED host memory stay where they are: the
+        kernel reads them in place over PCIe (zero copy), which moves only the bytes inside the view boxes (about 30 % of a
+        450 x 450 frame at the pose pipeline's crop sizes) instead of whole frames.  Off by default: measured on B200 the
+        SMs' small PCIe reads reach ~7 GB/s, the copy engine 50 GB/s, so copying whole frames is ~2x faster at config 2
+        (profiles/README.md); it pays only when the view boxes are a small fraction of much larger frames."""
+        if not self.zero_copy_frames:
+            return batch.to(self.device, non_blocking=True)
+        cats = batch.meta.categories
+
+        def keep_on_host(k, v):
+            if E.as_category(cats.get(k)) != E.FieldCategory.image:
+                return False
+            ts = v if isinstance(v, (list, tuple)) else [v]
+            return all(isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and not t.is_cuda and t.is_pinned() for t in ts)
+
+        out = batch.__class__(batch.meta, {})
+        for k, v in batch.items():
+            if keep_on_host(k, v):
+                out[k] = v
+            elif isinstance(v, (list, tuple)):
+                out[k] = [t.to(self.device, non_blocking=True) for t in v]
+            else:
+                out[k] = v.to(self.device, non_blocking=True)
+        return out
+
     def __call__(self, batch: Batch, params: Optional[AugmentationDraws] = None) -> Batch:
         if batch.meta.prefixshape == ():
             batch = batch.with_batchdim()
         (B,) = batch.meta.prefixshape
         if batch.device != self.device:
-            batch = batch.to(self.device, non_blocking=True)
+            batch = self._to_device(batch)
         d = params if params is not None else self.draw(B)
         res = E.fused_forward(batch, flags=self.flags, out_size=self.inputsize, geo=d.geo, do_flip=d.do_flip,
                               rot_dir=d.rot_dir, photo=d.photo, rowbuf_capacity=self.rowbuf_capacity)

@@ -226,3 +226,30 @@ def test_full_size_config2_properties():
         err = np.abs(img[i].cpu().numpy() - want["image"][0]).max()
         assert err <= 1.0 / 255, (i, err)
         np.testing.assert_allclose(whole.batch["pt3d_68"][i].cpu().numpy(), want["pt3d_68"][0], rtol=1e-4, atol=2e-5)
+
+
+def test_zero_copy_pinned_frames_equal_device_frames():
+    """Source frames left in pinned host memory (the kernel reads the view boxes in place over PCIe) give bit-identical
+    results to frames copied to the device first; pageable host frames are refused by the engine."""
+    import bench
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
+    from trackertraincode_b200.datatransformation import FusedPoseAugmentation, _engine as E
+
+    B = 64
+    host = bench.make_host_batch(9, B)
+    cats = {k: FieldCategory(v) for k, v in bench.CATS.items()}
+    pinned = Batch(Metadata((bench.SRC, bench.SRC), B, "t", None, dict(cats)), {k: torch.from_numpy(v).pin_memory() for k, v in host.items()})
+    outs = []
+    for zc in (True, False):
+        aug = FusedPoseAugmentation(S, rotation_aug_angle=30.0, device="cuda", seed=5, zero_copy_frames=zc)
+        torch.manual_seed(11)
+        np.random.seed(11)
+        draws = aug.draw(B)
+        outs.append(aug(pinned, params=draws))
+    assert outs[0]["image"].is_cuda and torch.equal(outs[0]["image"], outs[1]["image"])
+    for k in ("roi", "coord", "pose", "pt3d_68"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    pageable = Batch(pinned.meta, {k: (torch.from_numpy(v) if k == "image" else torch.from_numpy(v).cuda()) for k, v in host.items()})
+    with pytest.raises(N.NativeError):
+        E.fused_forward(pageable, flags=N.F_NORMALIZE, out_size=S)
