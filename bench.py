@@ -350,18 +350,20 @@ def run_gpu_arm(args):
     host_outs = [host_out, {k: torch.empty_like(v).pin_memory() for k, v in host_out.items()}]
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
 
-    def measure_e2e(zero_copy: bool, pipelined: bool):
+    def measure_e2e(zero_copy: bool, pipelined: bool, bands: bool = False):
         """Public API from pinned host buffers: per step the host->device copy of the step's frames + labels, the fused
         launch, and the device->host read of the step's labels.  pipelined: two streams alternate, the host waits for step
         s - 1 after enqueuing step s (what a prefetching loader does), so the copy engine never idles; otherwise one stream,
         synchronised every step.  zero_copy: the frames stay in pinned host memory and the kernel reads them in place."""
         aug = FusedPoseAugmentation(OUT, rotation_aug_angle=30.0, roi_override="original", enable_image_aug=True, device=dev,
-                                    zero_copy_frames=zero_copy)
+                                    zero_copy_frames=zero_copy, upload_row_bands=bands)
+        rows = []
 
         def e2e_step(s):
             st = streams[s % 2] if pipelined else torch.cuda.current_stream(dev)
             with torch.cuda.stream(st):
                 out = aug(pinned[s % 2])
+                rows.append(aug.uploaded_rows)
                 for k in label_keys:
                     host_outs[s % 2][k].copy_(out[k], non_blocking=True)
             if pipelined:
@@ -381,12 +383,13 @@ def run_gpu_arm(args):
             t = torch.tensor([e2e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        return world * BATCH * e2e_steps / e2e_s
+        return world * BATCH * e2e_steps / e2e_s, float(np.mean(rows[-e2e_steps:]))
 
-    e2e_sync = measure_e2e(False, False)
-    e2e_zero_copy = measure_e2e(True, False)
-    e2e_value = measure_e2e(False, True)
-    h2d = label_bytes + frame_bytes
+    e2e_sync, _ = measure_e2e(False, False)
+    e2e_zero_copy, _ = measure_e2e(True, False)
+    e2e_full, _ = measure_e2e(False, True)
+    e2e_value, band_rows = measure_e2e(False, True, bands=True)
+    h2d = label_bytes + int(band_rows * SRC)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -415,10 +418,13 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
-                    "note": "pinned host frames+labels -> FusedPoseAugmentation (Batch.to(device), host param sampling, one fused "
-                            "launch) -> labels read back into pinned host memory; two streams alternate and the host waits for step "
-                            "s-1 after enqueuing step s, as a prefetching loader does",
-                    "synchronised_every_step": {"value": e2e_sync},
+                    "note": "pinned host frames+labels -> FusedPoseAugmentation (host param sampling; host->device copy of the labels "
+                            "and of the frame rows the sampled view boxes touch, b200aug_upload_row_bands; one fused launch) -> labels "
+                            "read back into pinned host memory; two streams alternate and the host waits for step s-1 after enqueuing "
+                            "step s, as a prefetching loader does",
+                    "whole_frames": {"value": e2e_full, "h2d_bytes_per_step": label_bytes + frame_bytes,
+                                     "note": "same, whole frames copied (upload_row_bands=False)"},
+                    "whole_frames_synchronised_every_step": {"value": e2e_sync},
                     "zero_copy_frames": {"value": e2e_zero_copy, "h2d_bytes_per_step": label_bytes + int(alg_bytes - BATCH * (OUT * OUT * 4 + LABEL_BYTES)),
                                          "note": "frames left in pinned host memory and read in place by the kernel (only the view "
                                                  "boxes cross PCIe), synchronised every step"}},

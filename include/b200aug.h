@@ -170,6 +170,14 @@ size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capacity);
 /* bytes of scratch per sample that hold the rotated canvas of a crop box of up to max_side x max_side source pixels */
 int64_t b200aug_workspace_stride(int max_side);
 
+/* Host -> device upload of the rows the fused kernel will read, instead of whole frames (Batch.to(device),
+ * datasets/batch.py:161-165 / pipelines.py:508): for each of `batch` stacked frames (host_frames: PINNED host memory,
+ * [batch] frames of frame_stride bytes, rows of `pitch` bytes) the rows [row_lo[i], row_hi[i]) are copied to the same
+ * offsets of dev_frames (device, same layout) with the copy engine, stream-ordered.  row_lo / row_hi are HOST arrays; rows
+ * outside the band keep whatever dev_frames held.  The caller derives the bands from the sampled view boxes. */
+int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
+                             int32_t batch, const int32_t* row_lo, const int32_t* row_hi, void* stream);
+
 /* The fused hot path: one launch, one CTA per sample.
  * Replaces, per the flags: batch/normalization.py:83-90, batch/misc.py:9-31, batch/geometric.py:107-231
  * (+ tensors/image_geometric_cv2.py:28-155 incl. cv2.warpAffine / cv2.resize arithmetic, tensors/affinetrafo.py:37-148),

@@ -18,6 +18,8 @@
 // is the uint8 histogram pushed through the LUT prefix); only the 5x5 blur needs neighbours.  The output pass streams
 // the tile through LUT [+blur] [+noise, Philox] [+clip] [-0.5] into coalesced float32 stores.
 #include <cuda_runtime.h>
+#include <vector>
+#include <cstdlib>
 #include <math.h>
 #include <stdint.h>
 
@@ -1808,6 +1810,41 @@ extern "C" int64_t b200aug_workspace_stride(int max_side) {
   if (max_side <= 0) return 0;
   const int64_t spitch = (max_side + 16 + 15) & ~15;
   return ((spitch * (max_side + 1)) + 255) & ~int64_t(255);
+}
+
+extern "C" int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
+                                        int32_t batch, const int32_t* row_lo, const int32_t* row_hi, void* stream) {
+  if (!dev_frames || !host_frames || frame_stride <= 0 || pitch <= 0 || batch < 0 || !row_lo || !row_hi) return B200AUG_E_INVALID_ARG;
+  std::vector<void*> dsts, srcs;
+  std::vector<size_t> sizes;
+  dsts.reserve(batch); srcs.reserve(batch); sizes.reserve(batch);
+  for (int i = 0; i < batch; ++i) {
+    const int64_t lo = row_lo[i], hi = row_hi[i];
+    if (lo < 0 || hi * pitch > frame_stride) return B200AUG_E_INVALID_ARG;
+    if (hi <= lo) continue;
+    const int64_t off = (int64_t)i * frame_stride + lo * pitch;
+    dsts.push_back(dev_frames + off);
+    srcs.push_back(const_cast<uint8_t*>(host_frames) + off);
+    sizes.push_back((size_t)((hi - lo) * pitch));
+  }
+  if (dsts.empty()) return B200AUG_OK;
+  // one batched submission (CUDA 12.8+); it is refused on the legacy default stream, where the copies go one by one
+  static const bool one_by_one = getenv("B200AUG_UPLOAD_ONE_BY_ONE") != nullptr;
+  cudaError_t e = cudaErrorNotSupported;
+  if (stream && !one_by_one) {
+    cudaMemcpyAttributes attr = {};
+    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t attr_idx = 0, fail = 0;
+    e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr, &attr_idx, 1, &fail, (cudaStream_t)stream);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    for (size_t i = 0; i < dsts.size(); ++i) {
+      e = cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, (cudaStream_t)stream);
+      if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+    }
+  }
+  return B200AUG_OK;
 }
 
 static int check_fields(int n, const B200AugField* f) {

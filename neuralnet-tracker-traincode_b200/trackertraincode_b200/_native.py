@@ -48,7 +48,7 @@ class FusedArgs(C.Structure):
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32")
+           "b200aug_workspace_stride", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32")
 
 
 class NativeError(RuntimeError):
@@ -68,6 +68,8 @@ def _load():
     lib.b200aug_fused_smem_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.b200aug_workspace_stride.restype = C.c_int64
     lib.b200aug_workspace_stride.argtypes = [C.c_int]
+    lib.b200aug_upload_row_bands.restype = C.c_int
+    lib.b200aug_upload_row_bands.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200aug_fused_forward.restype = C.c_int
     lib.b200aug_fused_forward.argtypes = [C.POINTER(FusedArgs), C.c_void_p]
     lib.b200aug_apply_affine2d.restype = C.c_int

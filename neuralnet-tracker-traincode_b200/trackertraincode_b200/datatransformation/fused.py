@@ -62,7 +62,7 @@ def draw_photo_params(B: int, seed: int, sample_offset: int) -> E.PhotoParams:
 class FusedPoseAugmentation:
     def __init__(self, inputsize: int = 129, rotation_aug_angle: float = 30.0, roi_override: str = "original",
                  enable_image_aug: bool = True, train: bool = True, p_rot: float = 0.01, device="cuda",
-                 seed: int = 0, rowbuf_capacity: int = 0, zero_copy_frames: bool = False):
+                 seed: int = 0, rowbuf_capacity: int = 0, zero_copy_frames: bool = False, upload_row_bands: bool = True):
         if roi_override not in ("original", "landmarks"):
             raise N.NativeError("roi_override='extent_to_forehead' needs the BFM face model and is not on the B200 path")
         ext = {"original": 1.1, "landmarks": 1.2}[roi_override]  # pipelines.py:334
@@ -83,6 +83,9 @@ class FusedPoseAugmentation:
         self.samples_seen = 0
         self.rowbuf_capacity = rowbuf_capacity
         self.zero_copy_frames = zero_copy_frames
+        self.upload_row_bands = upload_row_bands and not zero_copy_frames
+        self.uploaded_rows = 0   # rows copied host->device by the last call that used the row-band upload
+        self._frames = {}        # device frame stacks the row bands land in, per (shape, stream)
 
     def draw(self, B: int) -> AugmentationDraws:
         p = self.sampler((B,))
@@ -120,13 +123,62 @@ class FusedPoseAugmentation:
                 out[k] = v.to(self.device, non_blocking=True)
         return out
 
+    # ---- row-band upload ------------------------------------------------------------------------------------
+    def _row_bands(self, roi: torch.Tensor, d: AugmentationDraws, H: int, beyond_border_shift: float = 0.3):
+        """Rows of each frame the kernel can touch, conservatively: the view box of geometric.py:135-156 restated in float64
+        with 3 rows of margin (the kernel's float32 box differs by far less than a pixel); rotated samples read the
+        bounding box of the rotated square, at most size / sqrt(2) either side of the box centre for any angle."""
+        r = roi.detach().to("cpu", torch.float64).reshape(-1, 4).numpy()
+        f = d.geo.scales.detach().to("cpu", torch.float64).reshape(-1).numpy()
+        ry = d.geo.translations.detach().to("cpu", torch.float64).reshape(-1, 2).numpy()[:, 1]
+        rot = d.geo.angles.detach().to("cpu", torch.float64).reshape(-1).numpy() != 0.0
+        bw, bh = r[:, 2] - r[:, 0], r[:, 3] - r[:, 1]
+        size = np.maximum(bw, bh) * f
+        wy = 0.5 * np.abs(size - bh) + beyond_border_shift * np.minimum(size, bh)
+        cy = 0.5 * (r[:, 3] + r[:, 1]) + wy * ry
+        half = np.where(rot, size * 0.70711 + 1.0, size * 0.5)
+        lo = np.clip(np.floor(cy - half) - 3, 0, H).astype(np.int32)
+        hi = np.clip(np.ceil(cy + half) + 3, 0, H).astype(np.int32)
+        return np.ascontiguousarray(lo), np.ascontiguousarray(np.maximum(hi, lo))
+
+    def _upload(self, batch: Batch, d: AugmentationDraws) -> Batch:
+        """Batch.to(device) (pipelines.py:508).  With `upload_row_bands` and stacked frames in pinned host memory only the
+        rows the sampled view boxes touch are copied (b200aug_upload_row_bands): ~60 % of a 450 x 450 frame at the pose
+        pipeline's crop sizes, and the host->device copy is what bounds the end-to-end rate."""
+        cats = batch.meta.categories
+        img_keys = [k for k, v in batch.items() if E.as_category(cats.get(k)) == E.FieldCategory.image]
+        ok = (self.upload_row_bands and (self.flags & N.F_FOCUS) and not (self.flags & N.F_ROI_FROM_LANDMARKS) and len(img_keys) == 1
+              and "roi" in batch.keys())
+        img = batch[img_keys[0]] if ok else None
+        ok = ok and isinstance(img, torch.Tensor) and img.dtype == torch.uint8 and not img.is_cuda and img.is_pinned() and img.is_contiguous() \
+            and (img.dim() == 3 or (img.dim() == 4 and (img.shape[-1] == 1 or img.shape[1] == 1)))
+        if not ok:
+            return self._to_device(batch)
+        B = img.shape[0]
+        H, W = (img.shape[1], img.shape[2]) if (img.dim() == 3 or img.shape[-1] == 1) else (img.shape[2], img.shape[3])
+        lo, hi = self._row_bands(batch["roi"], d, H)
+        stream = torch.cuda.current_stream(self.device)
+        key = (tuple(img.shape), stream.cuda_stream)
+        frames = self._frames.get(key)
+        if frames is None:
+            frames = self._frames[key] = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.b200aug_upload_row_bands(frames.data_ptr(), img.data_ptr(), H * W, W, B, lo.ctypes.data, hi.ctypes.data,
+                                                   stream.cuda_stream), "b200aug_upload_row_bands")
+        self.uploaded_rows = int((hi - lo).sum())
+        out = batch.__class__(batch.meta, {})
+        for k, v in batch.items():
+            out[k] = frames if k == img_keys[0] else (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else
+                                                     [t.to(self.device, non_blocking=True) for t in v])
+        return out
+
     def __call__(self, batch: Batch, params: Optional[AugmentationDraws] = None) -> Batch:
         if batch.meta.prefixshape == ():
             batch = batch.with_batchdim()
         (B,) = batch.meta.prefixshape
-        if batch.device != self.device:
-            batch = self._to_device(batch)
         d = params if params is not None else self.draw(B)
+        if batch.device != self.device:
+            batch = self._upload(batch, d)
         res = E.fused_forward(batch, flags=self.flags, out_size=self.inputsize, geo=d.geo, do_flip=d.do_flip,
                               rot_dir=d.rot_dir, photo=d.photo, rowbuf_capacity=self.rowbuf_capacity)
         self.samples_seen += B

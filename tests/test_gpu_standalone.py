@@ -228,28 +228,36 @@ def test_full_size_config2_properties():
         np.testing.assert_allclose(whole.batch["pt3d_68"][i].cpu().numpy(), want["pt3d_68"][0], rtol=1e-4, atol=2e-5)
 
 
-def test_zero_copy_pinned_frames_equal_device_frames():
-    """Source frames left in pinned host memory (the kernel reads the view boxes in place over PCIe) give bit-identical
-    results to frames copied to the device first; pageable host frames are refused by the engine."""
+def test_upload_modes_agree():
+    """Three ways of getting pinned host frames to the kernel give bit-identical results: whole frames copied
+    (Batch.to), only the row bands of the sampled view boxes copied (b200aug_upload_row_bands; the rest of the device
+    frame stack holds stale rows of the previous batch), and frames read in place from pinned host memory.  Pageable
+    host frames are refused by the engine."""
     import bench
     from trackertraincode_b200 import _native as N
     from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
     from trackertraincode_b200.datatransformation import FusedPoseAugmentation, _engine as E
 
-    B = 64
-    host = bench.make_host_batch(9, B)
+    B = 128
     cats = {k: FieldCategory(v) for k, v in bench.CATS.items()}
-    pinned = Batch(Metadata((bench.SRC, bench.SRC), B, "t", None, dict(cats)), {k: torch.from_numpy(v).pin_memory() for k, v in host.items()})
-    outs = []
-    for zc in (True, False):
-        aug = FusedPoseAugmentation(S, rotation_aug_angle=30.0, device="cuda", seed=5, zero_copy_frames=zc)
-        torch.manual_seed(11)
-        np.random.seed(11)
-        draws = aug.draw(B)
-        outs.append(aug(pinned, params=draws))
-    assert outs[0]["image"].is_cuda and torch.equal(outs[0]["image"], outs[1]["image"])
-    for k in ("roi", "coord", "pose", "pt3d_68"):
-        assert torch.equal(outs[0][k], outs[1][k]), k
+    augs = {m: FusedPoseAugmentation(S, rotation_aug_angle=30.0, device="cuda", seed=5, zero_copy_frames=(m == "zero_copy"),
+                                     upload_row_bands=(m == "bands")) for m in ("copy", "bands", "zero_copy")}
+    for rnd in range(3):  # the band uploads of later rounds land in a frame stack full of the earlier rounds' rows
+        host = bench.make_host_batch(9 + rnd, B)
+        if rnd == 1:  # boxes hanging over the frame borders
+            host["roi"][:, [1, 3]] += np.where(np.arange(B) % 2 == 0, -120.0, 150.0).astype(np.float32)[:, None]
+        pinned = Batch(Metadata((bench.SRC, bench.SRC), B, "t", None, dict(cats)), {k: torch.from_numpy(v).pin_memory() for k, v in host.items()})
+        outs = {}
+        for m, aug in augs.items():
+            torch.manual_seed(11 + rnd)
+            np.random.seed(11 + rnd)
+            draws = aug.draw(B)
+            outs[m] = aug(pinned, params=draws)
+        assert 0 < augs["bands"].uploaded_rows < 0.8 * B * bench.SRC
+        for m in ("bands", "zero_copy"):
+            assert outs[m]["image"].is_cuda and torch.equal(outs[m]["image"], outs["copy"]["image"]), (rnd, m)
+            for k in ("roi", "coord", "pose", "pt3d_68"):
+                assert torch.equal(outs[m][k], outs["copy"][k]), (rnd, m, k)
     pageable = Batch(pinned.meta, {k: (torch.from_numpy(v) if k == "image" else torch.from_numpy(v).cuda()) for k, v in host.items()})
     with pytest.raises(N.NativeError):
         E.fused_forward(pageable, flags=N.F_NORMALIZE, out_size=S)
