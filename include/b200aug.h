@@ -198,6 +198,22 @@ int b200aug_apply_affine2d(const float* tr, int64_t tr_stride, int batch, int n_
 int b200aug_photometric_f32(const float* in, float* out, float* tmp, int batch, int width, int height,
                             const B200AugPhotoParams* photo, float bias, void* stream);
 
+/* PerspectiveCorrector.corrected_rotation (eval.py:491-529) with _make_look_at_matrix (eval.py:531-544),
+ * torchquaternion.from_matrix (neuralnets/torchquaternion.py:94-168) and torchquaternion.mult (:40-48):
+ *   xy_n = (coord.xy - half_size) / (div_x, div_y);  M = look_at([xy_n, f]);  out = from_matrix(M) (x) pose   (xyzw).
+ * half_sizes: [B,2] (size_stride 2) or one [2] shared by the batch (size_stride 0); coord rows are coord_stride floats
+ * apart (>= 2).  The reference divides BOTH axes by `half_image_size_tensor[0]` (eval.py:525) -- the half width for a [2]
+ * size, row 0 of the batch for a [B,2] size; the caller passes that divisor pair.  out [B,4] and / or look_at_out [B,3,3]
+ * (row-major, columns x, y, z) are written; either may be NULL.  With half_sizes == NULL the rows of coord (>= 3 floats)
+ * are taken as the look-at positions themselves (PerspectiveCorrector._make_look_at_matrix on its own). */
+int b200aug_corrected_rotation(const float* half_sizes, int64_t size_stride, float div_x, float div_y, float f,
+                               const float* coord, int64_t coord_stride, const float* pose, float* out, float* look_at_out,
+                               int batch, void* stream);
+
+/* torchquaternion.tomatrix (to_matrix != 0: in [B,4] xyzw -> out [B,3,3]; torchquaternion.py:70-91, the matrix / 6D
+ * rotation target of losses.py:53-58) or torchquaternion.from_matrix (to_matrix == 0: in [B,3,3] -> out [B,4]; :94-168). */
+int b200aug_quat_matrix(const float* in, float* out, int batch, int to_matrix, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

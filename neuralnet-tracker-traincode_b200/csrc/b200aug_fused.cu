@@ -1781,6 +1781,120 @@ __global__ void apply_affine2d_kernel(const float* __restrict__ tr, int64_t tr_s
 
 using namespace b200aug;
 
+// ------------------------------------------------------------------------------------------------ rotation labels (eval side)
+
+// torchquaternion.mult (neuralnets/torchquaternion.py:23-48), xyzw: the 4x4 matrix form of u times the (w,i,j,k) vector of v
+__device__ __forceinline__ void quat_mult(const float* u, const float* v, float* o) {
+  const float ui = u[0], uj = u[1], uk = u[2], uw = u[3], vi = v[0], vj = v[1], vk = v[2], vw = v[3];
+  const float w = add(add(add(mul(uw, vw), mul(-ui, vi)), mul(-uj, vj)), mul(-uk, vk));
+  const float i = add(add(add(mul(ui, vw), mul(uw, vi)), mul(-uk, vj)), mul(uj, vk));
+  const float j = add(add(add(mul(uj, vw), mul(uk, vi)), mul(uw, vj)), mul(-ui, vk));
+  const float k = add(add(add(mul(uk, vw), mul(-uj, vi)), mul(ui, vj)), mul(uw, vk));
+  o[0] = i; o[1] = j; o[2] = k; o[3] = w;
+}
+
+// torchquaternion.from_matrix (torchquaternion.py:94-168): four candidate solutions, the best conditioned one is picked
+// (first maximum of the clamped square-root arguments), then positivereal() (q * sign(w); sign(0) = 0 as in torch)
+__device__ void quat_from_matrix(const float (&m)[3][3], float* q) {
+  float arg[4];
+  arg[0] = add(add(add(-m[0][0], -m[1][1]), m[2][2]), 1.f);   // k
+  arg[1] = add(add(add(-m[0][0], m[1][1]), -m[2][2]), 1.f);   // j
+  arg[2] = add(add(add(m[0][0], -m[1][1]), -m[2][2]), 1.f);   // i
+  arg[3] = add(add(add(m[0][0], m[1][1]), m[2][2]), 1.f);     // w
+  int pick = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    arg[t] = fmaxf(arg[t], 1.0e-6f);
+    if (arg[t] > arg[pick]) pick = t;
+  }
+  const float d = mul(sqrtf(arg[pick]), 0.5f);
+  auto val = [&](float a, float b) { return fdiv(mul(0.25f, add(a, b)), d); };
+  float qi, qj, qk, qw;
+  switch (pick) {
+    case 0: qw = val(m[1][0], -m[0][1]); qi = val(m[2][0], m[0][2]); qj = val(m[1][2], m[2][1]); qk = d; break;
+    case 1: qw = val(m[0][2], -m[2][0]); qi = val(m[1][0], m[0][1]); qk = val(m[1][2], m[2][1]); qj = d; break;
+    case 2: qw = val(m[2][1], -m[1][2]); qj = val(m[1][0], m[0][1]); qk = val(m[0][2], m[2][0]); qi = d; break;
+    default: qi = val(m[2][1], -m[1][2]); qj = val(m[0][2], -m[2][0]); qk = val(m[1][0], -m[0][1]); qw = d; break;
+  }
+  const float sg = (qw > 0.f) ? 1.f : ((qw < 0.f) ? -1.f : 0.f);
+  q[0] = mul(qi, sg); q[1] = mul(qj, sg); q[2] = mul(qk, sg); q[3] = mul(qw, sg);
+}
+
+// PerspectiveCorrector._make_look_at_matrix (eval.py:531-544), columns x, y, z; note y / |x| as in the reference (:542)
+__device__ void look_at_matrix(float px, float py, float pz, float (&m)[3][3]) {
+  const float n = sqrtf(add(add(mul(px, px), mul(py, py)), mul(pz, pz)));
+  const float zx = fdiv(px, n), zy = fdiv(py, n), zz = fdiv(pz, n);
+  // cross((0,1,0), z) = (zz, 0, -zx)
+  float xx = zz, xy = 0.f, xz = -zx;
+  const float nx = sqrtf(add(add(mul(xx, xx), mul(xy, xy)), mul(xz, xz)));
+  xx = fdiv(xx, nx); xy = fdiv(xy, nx); xz = fdiv(xz, nx);
+  float yx = sub(mul(zy, xz), mul(zz, xy)), yy = sub(mul(zz, xx), mul(zx, xz)), yz = sub(mul(zx, xy), mul(zy, xx));
+  const float nx2 = sqrtf(add(add(mul(xx, xx), mul(xy, xy)), mul(xz, xz)));
+  yx = fdiv(yx, nx2); yy = fdiv(yy, nx2); yz = fdiv(yz, nx2);
+  m[0][0] = xx; m[1][0] = xy; m[2][0] = xz;
+  m[0][1] = yx; m[1][1] = yy; m[2][1] = yz;
+  m[0][2] = zx; m[1][2] = zy; m[2][2] = zz;
+}
+
+// PerspectiveCorrector.corrected_rotation (eval.py:491-529): one thread per sample
+__global__ void corrected_rotation_kernel(const float* __restrict__ half_sizes, int64_t size_stride, float div_x, float div_y, float f,
+                                          const float* __restrict__ coord, int64_t coord_stride, const float* __restrict__ pose,
+                                          float* __restrict__ out, float* __restrict__ look_at_out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xn, yn, zn = f;
+  if (half_sizes) {
+    const float hx = half_sizes[i * size_stride], hy = half_sizes[i * size_stride + 1];
+    xn = fdiv(sub(coord[i * coord_stride], hx), div_x);
+    yn = fdiv(sub(coord[i * coord_stride + 1], hy), div_y);
+  } else {  // coord rows are the look-at positions themselves
+    xn = coord[i * coord_stride];
+    yn = coord[i * coord_stride + 1];
+    zn = coord[i * coord_stride + 2];
+  }
+  float m[3][3];
+  look_at_matrix(xn, yn, zn, m);
+  if (look_at_out)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) look_at_out[(size_t)i * 9 + r * 3 + c] = m[r][c];
+  if (out) {
+    float qm[4], qo[4];
+    quat_from_matrix(m, qm);
+    const float qp[4] = {pose[4 * (size_t)i], pose[4 * (size_t)i + 1], pose[4 * (size_t)i + 2], pose[4 * (size_t)i + 3]};
+    quat_mult(qm, qp, qo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[4 * (size_t)i + k] = qo[k];
+  }
+}
+
+// torchquaternion.tomatrix (torchquaternion.py:70-91; the 6D / matrix target of losses.py:53-58) and from_matrix
+__global__ void quat_matrix_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int to_matrix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (to_matrix) {
+    const float qi = in[4 * (size_t)i], qj = in[4 * (size_t)i + 1], qk = in[4 * (size_t)i + 2], qw = in[4 * (size_t)i + 3];
+    float* o = out + 9 * (size_t)i;
+    o[0] = sub(1.f, mul(2.f, add(mul(qj, qj), mul(qk, qk))));
+    o[3] = mul(2.f, add(mul(qi, qj), mul(qk, qw)));
+    o[6] = mul(2.f, sub(mul(qi, qk), mul(qj, qw)));
+    o[1] = mul(2.f, sub(mul(qi, qj), mul(qk, qw)));
+    o[4] = sub(1.f, mul(2.f, add(mul(qi, qi), mul(qk, qk))));
+    o[7] = mul(2.f, add(mul(qj, qk), mul(qi, qw)));
+    o[2] = mul(2.f, add(mul(qi, qk), mul(qj, qw)));
+    o[5] = mul(2.f, sub(mul(qj, qk), mul(qi, qw)));
+    o[8] = sub(1.f, mul(2.f, add(mul(qi, qi), mul(qj, qj))));
+  } else {
+    float m[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m[r][c] = in[9 * (size_t)i + 3 * r + c];
+    quat_from_matrix(m, out + 4 * (size_t)i);
+  }
+}
+
 static thread_local int g_last_cuda_error = 0;
 
 extern "C" int b200aug_abi_version(void) { return B200AUG_ABI_VERSION; }
@@ -1943,6 +2057,28 @@ extern "C" int b200aug_photometric_f32(const float* in, float* out, float* tmp, 
   if (blur && in == out) return B200AUG_E_INVALID_ARG;
   if (batch == 0) return B200AUG_OK;
   photometric_f32_kernel<<<batch, NTHREADS, 0, (cudaStream_t)stream>>>(in, out, tmp, width, height, *photo, bias);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  return B200AUG_OK;
+}
+
+extern "C" int b200aug_corrected_rotation(const float* half_sizes, int64_t size_stride, float div_x, float div_y, float f,
+                                          const float* coord, int64_t coord_stride, const float* pose, float* out,
+                                          float* look_at_out, int batch, void* stream) {
+  if (!coord || batch < 0 || (!out && !look_at_out) || (out && !pose) || size_stride < 0 || coord_stride < (half_sizes ? 2 : 3))
+    return B200AUG_E_INVALID_ARG;
+  if (batch == 0) return B200AUG_OK;
+  corrected_rotation_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(half_sizes, size_stride, div_x, div_y, f, coord,
+                                                                                  coord_stride, pose, out, look_at_out, batch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  return B200AUG_OK;
+}
+
+extern "C" int b200aug_quat_matrix(const float* in, float* out, int batch, int to_matrix, void* stream) {
+  if (!in || !out || batch < 0) return B200AUG_E_INVALID_ARG;
+  if (batch == 0) return B200AUG_OK;
+  quat_matrix_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, out, batch, to_matrix);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
   return B200AUG_OK;

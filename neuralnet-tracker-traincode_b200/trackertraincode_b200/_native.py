@@ -48,7 +48,8 @@ class FusedArgs(C.Structure):
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32")
+           "b200aug_workspace_stride", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
+           "b200aug_quat_matrix")
 
 
 class NativeError(RuntimeError):
@@ -77,6 +78,11 @@ def _load():
     lib.b200aug_photometric_f32.restype = C.c_int
     lib.b200aug_photometric_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(PhotoParams),
                                             C.c_float, C.c_void_p]
+    lib.b200aug_corrected_rotation.restype = C.c_int
+    lib.b200aug_corrected_rotation.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200aug_quat_matrix.restype = C.c_int
+    lib.b200aug_quat_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     if lib.b200aug_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {lib.b200aug_abi_version()} vs binding {ABI_VERSION}")
     return lib
