@@ -302,7 +302,8 @@ def run_gpu_arm(args):
         geo = E.GeoParams(torch.from_numpy(gp.scales), an, torch.from_numpy(gp.translations), E.host_cos_sin(an))
         calls.append(E.prepare_fused(device_batch(h), flags=flags, out_size=OUT, geo=geo,
                                      do_flip=torch.from_numpy(gp.do_flip.astype(np.uint8)), rot_dir=torch.from_numpy(gp.rot_dir),
-                                     photo=to_photo(pp), want_status=True, rowbuf_capacity=args.rowbuf))
+                                     photo=to_photo(pp), want_status=True, rowbuf_capacity=args.rowbuf,
+                                     cluster_size=int(os.environ.get("B200AUG_BENCH_CLUSTER", "0"))))
     alg_bytes = float(np.mean([algorithmic_bytes(h, gp) for h, (gp, _) in zip(hosts, params)]))
     stream = torch.cuda.current_stream(dev)
 

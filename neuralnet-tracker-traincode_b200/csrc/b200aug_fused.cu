@@ -37,9 +37,10 @@ constexpr int TAIL_COLS = 8;       // a last group of at most this many columns 
 constexpr int KMAX = 6;            // widest INTER_AREA tap count the register path unrolls (scale factors up to ~5)
 constexpr int ROWBUF_SLACK = 16;   // the word-wise tap fetch may touch up to 11 bytes past the last tap
 constexpr int DT_CAP = 512;        // widest warp canvas with per-column delta tables in shared memory
-constexpr int DEFAULT_ROWBUF = 3584;  // per-warp staging bytes: a ring of RING_D crop-row segments in flight (up to 850 B each:
-                                      // 160 output columns at scale factors up to ~5), or one staged warpAffine tile
-                                      // footprint (39 rows x 64 B)
+constexpr int DEFAULT_ROWBUF = 2800;  // per-warp staging bytes: a ring of RING_D crop-row segments in flight (up to 690 B each:
+                                      // 128 output columns at scale factors up to ~5), or one staged warpAffine tile
+                                      // footprint (a 32 x 16 tile rotated by up to 45 degrees: 36 rows x 64 B + shifts).
+                                      // Smaller than the 3.5 KB it could use: the shared memory not taken is L1 (2 % faster)
 constexpr int RING_D = 4;          // canvas rows in flight per warp (cp.async commit groups)
 constexpr int ROWPROG_CAP = 96;    // canvas rows one warp can stream per band (its vertical-pass program, 8 B per row)
 constexpr int DEFAULT_CLUSTER = 2;  // CTAs sharing one sample
