@@ -814,7 +814,8 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 // The canvas is always a crop here: rotated samples were turned into one by warp_canvas_to_scratch().
 template <int K>
 __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int ow_band, int warp, int lane, int cr, int cl) {
-  const int rows_lo = (cr * oh) / cl, rows_n = ((cr + 1) * oh) / cl - rows_lo;  // this CTA's band of output rows
+  const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4)
+  const int rows_lo = (cr * oh) >> cs, rows_n = (((cr + 1) * oh) >> cs) - rows_lo;  // this CTA's band of output rows
   const int dy_begin = rows_lo + (warp * rows_n) / NWARPS, dy_end = rows_lo + ((warp + 1) * rows_n) / NWARPS;
   if (dy_begin >= dy_end) return;
   // everything lives in this CTA's dynamic shared memory; deriving the pointers here keeps the address space known
@@ -1087,7 +1088,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   const int cr = (int)cr_u, cl = (int)cl_u;  // rank in / size of the cluster that shares this sample
   // launch order -> sample: the caller may schedule expensive samples (rotated, blurred) first so that the cheap ones
   // fill the tail of the grid
-  const int b = a.order ? a.order[blockIdx.x / cl] : (int)(blockIdx.x / cl);
+  const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4: checked at launch), divisions become shifts
+  const int b = a.order ? a.order[blockIdx.x >> cs] : (int)(blockIdx.x >> cs);
   const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // (lay_w, lay_h) = (out_w, out_h) when an image is produced; label-only launches use a 1 x 1 layout so that label
@@ -1212,12 +1214,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
 
   trace_mark(a, 1);
   // this CTA's band of output rows, and the bytes the other CTAs of the cluster will bulk-copy into this tile
-  const int rows_lo = (cr * oh) / cl, rows_hi = ((cr + 1) * oh) / cl;
+  const int rows_lo = (cr * oh) >> cs, rows_hi = ((cr + 1) * oh) >> cs;
   int rx_bytes = 0;
   if (cl > 1 && P.status == B200AUG_S_OK && P.rot_dir == 0) {
     for (int q = 0; q < cl; ++q) {
       if (q == cr) continue;
-      const int lo = ((q * oh) / cl) * ow, hi = (((q + 1) * oh) / cl) * ow, alo = min((lo + 15) & ~15, hi), ahi = max(hi & ~15, alo);
+      const int lo = ((q * oh) >> cs) * ow, hi = (((q + 1) * oh) >> cs) * ow, alo = min((lo + 15) & ~15, hi), ahi = max(hi & ~15, alo);
       rx_bytes += ahi - alo;
     }
     if (tid == 0 && rx_bytes)
@@ -1427,7 +1429,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   // ---- uint8 output (geometric stages only) --------------------------------------------------------------
   if (!(a.flags & B200AUG_F_NORMALIZE)) {
     uint8_t* out = a.image_u8_out + (size_t)b * npix;
-    for (int p = (cr * npix) / cl + tid; p < ((cr + 1) * npix) / cl; p += NTHREADS) out[p] = tile[p];
+    for (int p = ((cr * npix) >> cs) + tid; p < (((cr + 1) * npix) >> cs); p += NTHREADS) out[p] = tile[p];
     trace_mark(a, 4);
     return;
   }
@@ -1514,7 +1516,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   // ---- output pass ----------------------------------------------------------------------------------------
   float* out = a.image_f32_out + (size_t)b * npix;
   const int Q = (npix + 3) >> 2;
-  const int g_lo = (cr * Q) / cl, g_hi = ((cr + 1) * Q) / cl;  // this CTA's share of the output
+  const int g_lo = (cr * Q) >> cs, g_hi = ((cr + 1) * Q) >> cs;  // this CTA's share of the output
   if (folded) {
     for (int g = g_lo + tid; g < g_hi; g += NTHREADS) {
 #pragma unroll

@@ -123,6 +123,23 @@ class FusedPoseAugmentation:
                 out[k] = v.to(self.device, non_blocking=True)
         return out
 
+    @staticmethod
+    def _account_for_video(meta, d: AugmentationDraws) -> AugmentationDraws:
+        """geometric.py:180-191: every frame of a clip gets the crop draw of the clip's first frame; the flip / rot90 draw is
+        per sample in the reference (geometric.py:234-237, applied before collation), i.e. also one per clip."""
+        if getattr(meta, "seq", None) is None:
+            return d
+        g = d.geo
+        for a, b in meta.sequence_start_end:
+            g.translations[a:b, ...] = g.translations[a:a + 1, ...]
+            g.scales[a:b] = g.scales[a:a + 1]
+            if g.angles is not None:
+                g.angles[a:b] = g.angles[a:a + 1]
+            d.do_flip[a:b] = d.do_flip[a:a + 1]
+            d.rot_dir[a:b] = d.rot_dir[a:a + 1]
+        d.geo = E.GeoParams(g.scales, g.angles, g.translations, E.host_cos_sin(g.angles))
+        return d
+
     # ---- row-band upload ------------------------------------------------------------------------------------
     def _row_bands(self, roi: torch.Tensor, d: AugmentationDraws, H: int, beyond_border_shift: float = 0.3):
         """Rows of each frame the kernel can touch, conservatively: the view box of geometric.py:135-156 restated in float64
@@ -176,7 +193,7 @@ class FusedPoseAugmentation:
         if batch.meta.prefixshape == ():
             batch = batch.with_batchdim()
         (B,) = batch.meta.prefixshape
-        d = params if params is not None else self.draw(B)
+        d = params if params is not None else self._account_for_video(batch.meta, self.draw(B))
         if batch.device != self.device:
             batch = self._upload(batch, d)
         res = E.fused_forward(batch, flags=self.flags, out_size=self.inputsize, geo=d.geo, do_flip=d.do_flip,

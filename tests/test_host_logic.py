@@ -183,3 +183,40 @@ def test_sharding_helpers_single_process():
     ids = {sharding.global_sample_offset(s, k, 4, 256) for s in range(3) for k in range(4)}
     assert ids == {256 * i for i in range(12)}
     assert sharding.max_over_ranks(1.5) == 1.5
+
+
+def test_fused_augmentation_video_draws_and_row_bands():
+    """Host side of FusedPoseAugmentation: clips share the draw of their first frame (geometric.py:180-191); the row bands
+    handed to b200aug_upload_row_bands cover the rows of the oracle's integer view boxes (rotated samples: of the rotated
+    square), with margin, for every sample."""
+    from oracle import geometric as ogeo
+
+    aug = FusedPoseAugmentation(129, rotation_aug_angle=30.0, device="cpu")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    B = 512
+    d = aug.draw(B)
+    meta = Metadata((450, 450), 0, "v", (0, 100, 101, 512), {})
+    d = aug._account_for_video(meta, d)
+    for a, b in meta.sequence_start_end:
+        for t in (d.geo.scales, d.geo.angles, d.geo.translations, d.do_flip, d.rot_dir, d.geo.cos_sin):
+            assert bool((t[a:b] == t[a:a + 1]).all())
+    torch.manual_seed(1)
+    np.random.seed(1)
+    d = aug.draw(B)
+    rng = np.random.default_rng(3)
+    wh = rng.uniform(147, 250, (B, 2))
+    c = 225 + rng.uniform(-140, 140, (B, 2))  # many boxes hang over the frame
+    roi = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    lo, hi = aug._row_bands(torch.from_numpy(roi), d, 450)
+    v = ogeo.round_view_roi(ogeo.compute_view_roi(roi, d.geo.scales.numpy(), d.geo.translations.numpy())).astype(np.int64)
+    rot = d.geo.angles.numpy() != 0
+    side = (v[:, 2] - v[:, 0]).astype(np.float64)
+    cy = 0.5 * (v[:, 1] + v[:, 3])
+    ang = np.abs(d.geo.angles.numpy().astype(np.float64))
+    half = np.where(rot, 0.5 * side * (np.cos(ang) + np.sin(ang)) + 1.0, 0.5 * (v[:, 3] - v[:, 1]))
+    need_lo = np.clip(np.floor(cy - half), 0, 450)
+    need_hi = np.clip(np.ceil(cy + half) + 1, 0, 450)  # + 1: the second bilinear tap row
+    touched = need_hi > need_lo
+    assert (lo[touched] <= need_lo[touched]).all() and (hi[touched] >= need_hi[touched]).all()
+    assert lo.dtype == np.int32 and (hi >= lo).all() and (hi - lo).sum() < 0.75 * B * 450
