@@ -261,3 +261,15 @@ def test_upload_modes_agree():
     pageable = Batch(pinned.meta, {k: (torch.from_numpy(v) if k == "image" else torch.from_numpy(v).cuda()) for k, v in host.items()})
     with pytest.raises(N.NativeError):
         E.fused_forward(pageable, flags=N.F_NORMALIZE, out_size=S)
+
+
+def test_randomised_sweep_script():
+    """scripts/gpu_stress.py (ragged batches of odd frame sizes and pitches, rotations up to 45 degrees, output sizes 64 / 129 /
+    200, oracle with identical draws): four rounds here, `profiles/r01d_stress.log` holds a 16-round run."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_stress.py"), "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
