@@ -214,6 +214,17 @@ int b200aug_corrected_rotation(const float* half_sizes, int64_t size_stride, flo
  * rotation target of losses.py:53-58) or torchquaternion.from_matrix (to_matrix == 0: in [B,3,3] -> out [B,4]; :94-168). */
 int b200aug_quat_matrix(const float* in, float* out, int batch, int to_matrix, void* stream);
 
+/* JPEG -> grayscale source frames on the device: replaces `imdecode(blob, color=False)` = cv2.imdecode(blob, 0)
+ * (datasets/preprocessing.py:42-54) for the JPEG blobs of the HDF5 `varsize_image_buffer` format (datasets/dshdf5.py:59-113).
+ * Entropy decoding and IDCT are nvJPEG's (batched, luminance plane only); results match cv2 to the IDCT rounding (+-2 grey
+ * levels).  data[i] / lengths[i]: HOST pointers to the JPEG streams; dst[i]: DEVICE pointer to frame i (rows of pitch[i]
+ * bytes, size from b200aug_jpeg_info); the arrays data / lengths / dst / pitch themselves are host arrays.  Stream-ordered;
+ * one decoder state per host thread.  b200aug_jpeg_last_status() returns the nvjpegStatus_t of the last failure. */
+int b200aug_jpeg_info(const uint8_t* data, size_t length, int32_t* width, int32_t* height, int32_t* components);
+int b200aug_decode_jpeg_gray(const uint8_t* const* data, const size_t* lengths, int32_t batch, uint8_t* const* dst,
+                             const int32_t* pitch, void* stream);
+int b200aug_jpeg_last_status(void);
+
 #ifdef __cplusplus
 }
 #endif
