@@ -812,8 +812,12 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 // steady state carries no row classification: rows above the frame (zeros) / the fetched rows / rows below the frame or
 // the frame's last row when its over-read would leave the image (staged synchronously, zero padded).
 // The canvas is always a crop here: rotated samples were turned into one by warp_canvas_to_scratch().
-template <int K>
-__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int ow_band, int warp, int lane, int cr, int cl) {
+// DIRECT: the sample's photometric chain is one point function (no equalize / blur / noise) and there is no 90-degree
+// rotation, so the finished uint8 pixel goes through the (already built) LUT straight to the float32 output `gimg` --
+// no tile, no cluster exchange, no separate output pass.
+template <int K, bool DIRECT>
+__device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int ow_band, int warp, int lane, int cr, int cl,
+                                       float* __restrict__ gimg) {
   const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4)
   const int rows_lo = (cr * oh) >> cs, rows_n = (((cr + 1) * oh) >> cs) - rows_lo;  // this CTA's band of output rows
   const int dy_begin = rows_lo + (warp * rows_n) / NWARPS, dy_end = rows_lo + ((warp + 1) * rows_n) / NWARPS;
@@ -881,6 +885,9 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     const int nvalid = (gcols - lane + 31) >> 5;
     uint32_t trow32 = tile32 + (uint32_t)(tm.o + (g0 + lane) * tm.sb + dy_begin * tm.sa);
     int cstep = 32 * tm.sb;
+    // DIRECT: the same pixel as a float32 in global memory, and the LUT behind the plan in shared memory
+    float* grow = DIRECT ? gimg + (tm.o + (g0 + lane) * tm.sb + dy_begin * tm.sa) : nullptr;
+    const uint32_t lut32 = smem_u32(smem + ((sizeof(Plan) + 15) & ~size_t(15)));
     float w[RMAX][K];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
@@ -947,7 +954,17 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
 #pragma unroll
       for (int j = 0; j < RMAX; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(ba, h[j]));
       if (pr.x < 0.f) {
-        if (fin == 0) {
+        if (DIRECT) {
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) {
+            const uint32_t q = cvt_rni_sat_u8(acc[j]);
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(lut32 + 4u * q) : "memory");
+            if (j < nvalid) grow[j * cstep] = v;
+            acc[j] = __fmul_rn(pr.y, h[j]);
+          }
+          grow += row_sa;
+        } else if (fin == 0) {
 #pragma unroll
           for (int j = 0; j < RMAX; ++j) {
             const uint32_t q = cvt_rni_sat_u8(acc[j]);
@@ -1213,6 +1230,16 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   __syncthreads();
 
   trace_mark(a, 1);
+  // Samples whose photometric chain is a single point function (no equalize, blur or noise: more than half of the training
+  // draws, and every evaluation sample) get their LUT now: the INTER_AREA pass can then write float32 output directly
+  // (`direct` below).  The cluster barrier in front of the resampling orders these writes before their first use.
+  const bool lut_early = (a.flags & B200AUG_F_NORMALIZE) && a.image_f32_out && P.blur_pos < 0 && P.eq_pos < 0 && !P.any_noise;
+  if (lut_early) {
+    float xv = apply_point_ops(P, __fmul_rn((float)tid, 0.00390625f), 0, P.n_ops, eq_lut);
+    if ((a.flags & B200AUG_F_PHOTOMETRIC) && a.photo.clip) xv = fminf(fmaxf(xv, 0.f), 1.f);
+    if (a.flags & B200AUG_F_WHITEN) xv = __fsub_rn(xv, 0.5f);
+    lut[tid] = xv;
+  }
   // this CTA's band of output rows, and the bytes the other CTAs of the cluster will bulk-copy into this tile
   const int rows_lo = (cr * oh) >> cs, rows_hi = ((cr + 1) * oh) >> cs;
   int rx_bytes = 0;
@@ -1325,7 +1352,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
               ow_band > 0;
   if (fast) {
     // a warp's band of canvas rows must fit its vertical-pass program
-    const int rows_per_warp = (rows_hi - rows_lo + NWARPS - 1) / NWARPS;
+    // (the widest band of any CTA of the cluster: `fast` -- and with it `direct` -- must come out the same in all of them)
+    const int rows_per_warp = (((oh + cl - 1) >> cs) + 1 + NWARPS - 1) / NWARPS;
     const int sy_ceil = (rs == RS_AREA_INT) ? P.iscale_y : (int)ceil(P.scale_y);
     if ((rows_per_warp + 1) * sy_ceil + 2 > ROWPROG_CAP) fast = false;
   }
@@ -1337,9 +1365,16 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       if (RING_D * ring_slot_bytes(seg) > cap + ROWBUF_SLACK || seg + 30 > 64 * 16) fast = false;
     }
   }
+  // direct: no tile, no exchange, no output pass -- the resampling pass writes the float32 crop itself
+  const bool direct = fast && lut_early && rs == RS_AREA && P.fin == 0 && P.rot_dir == 0;
   if (fast) {
     const int kx = P.kx;
-#define B200AUG_BAND(KK) area_band<KK>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl)
+    float* const gimg = direct ? a.image_f32_out + (size_t)b * npix : nullptr;
+#define B200AUG_BAND(KK)                                                              \
+  do {                                                                                \
+    if (direct) area_band<KK, true>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg); \
+    else area_band<KK, false>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, nullptr);  \
+  } while (0)
     if (kx <= 3) B200AUG_BAND(3);
     else if (kx == 4) B200AUG_BAND(4);
     else B200AUG_BAND(6);
@@ -1372,7 +1407,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
           const float beta = area_alpha(k, yn, yhf, yhl, yaf, yam, yal);
           acc = (k == 0) ? __fmul_rn(beta, h) : __fadd_rn(acc, __fmul_rn(beta, h));
         }
-        tile[tm.o + dy * tm.sa + dx * tm.sb] = sat_u8_rint(acc);
+        const uint8_t q = sat_u8_rint(acc);
+        if (direct) gimg[tm.o + dy * tm.sa + dx * tm.sb] = lut[q];
+        else tile[tm.o + dy * tm.sa + dx * tm.sb] = q;
       }
     } else {
       for (int p = tid; p < (rows_hi - rows_lo) * tw; p += NTHREADS) {
@@ -1388,6 +1425,13 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     }
   } else {
     for (int p = tid; p < npix; p += NTHREADS) tile[p] = 0;
+  }
+  if (direct) {  // the crop is already in global memory; only the labels are left (both CTAs of the cluster take this exit)
+    trace_mark(a, 3);
+    if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
+    trace_mark(a, 9);
+    trace_mark(a, 4);
+    return;
   }
   // ---- cluster exchange: every CTA resampled a band of rows into its own tile; now each sends its band to the others.
   // Without a 90-degree rotation the band is a contiguous byte range of the tile: its 16-byte aligned interior goes as
