@@ -676,6 +676,24 @@ __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ d
     X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
     Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
   };
+  // Row stride of the staged box: WT_STRIDE + pm or WT_STRIDE + 16 + pm bytes, whichever spreads one canvas row's 32 taps
+  // over more shared-memory banks.  The taps walk a straight line (mi[0] px right, mi[3] px down per canvas pixel), so the
+  // bank pattern depends on slope and stride only: at pitch 450 (pm = 2) and -30 degrees a 66-byte stride makes lanes two
+  // rows apart land 16 words apart -- 7 wavefronts per byte load -- while 82 bytes gives 2 (and 66 gives 1 at +30 degrees).
+  int wt_stride = WT_STRIDE;
+  {
+    const int ix = (int)floor(P.mi[0] * (double)lane), iy = (int)floor(P.mi[3] * (double)lane) + 64;
+    int best = INT_MAX;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int e = WT_STRIDE + 16 * c + pm;
+      const unsigned word = (unsigned)(iy * e + ix) >> 2, bank = word & 31u;
+      const unsigned same_word = __match_any_sync(0xffffffffu, word), same_bank = __match_any_sync(0xffffffffu, bank);
+      const unsigned leaders = __ballot_sync(0xffffffffu, (__ffs(same_word) - 1) == lane);  // one lane per distinct word
+      const int degree = __reduce_max_sync(0xffffffffu, __popc(same_bank & leaders));      // wavefronts of this load
+      if (degree < best) { best = degree; wt_stride = WT_STRIDE + 16 * c; }
+    }
+  }
   for (int t = cr * NWARPS + warp; t < tiles_x * tiles_y; t += cl * NWARPS) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x_lo = tx * WT_W, y_lo = ty * WT_H;
@@ -691,14 +709,16 @@ __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ d
     const int by0 = min(min(iy0, iy1), min(iy2, iy3)), by1 = max(max(iy0, iy1), max(iy2, iy3)) + 1;
     const int nrows = by1 - by0 + 1;
     // Staged layout: box row r is copied as four 16-byte chunks starting at the aligned address at or below its first byte,
-    // to shared-memory offset S_r = 64 r + 16 ((c0 + r pm) >> 4), c0 = alignment shift of row 0, pm = pitch mod 16.  The byte
-    // of box row r, box column x then sits at c0 + r (64 + pm) + x: linear in r, so the gather needs no per-row shift.
+    // to shared-memory offset S_r = B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift of row 0, pm = pitch mod 16, B = 64 or
+    // 80.  The byte of box row r, box column x then sits at c0 + r (B + pm) + x: linear in r, so the gather needs no per-row shift.
     const uintptr_t gbase = reinterpret_cast<uintptr_t>(src) + (size_t)by0 * pitch + bx0;  // top-left of the box
     const int c0 = (int)(gbase & 15);
-    const int rstride = WT_STRIDE + pm;
+    auto fits = [&](int st) { return (nrows - 1) * st + 16 * ((c0 + (nrows - 1) * pm) >> 4) + WT_STRIDE <= stage_bytes; };
+    const int bstride = fits(wt_stride) ? wt_stride : WT_STRIDE;  // (a tall box falls back to the compact stride)
+    const int rstride = bstride + pm;
     // staged: inside the frame (and not on its last row: the 16-byte chunks may run past a row's end), small enough
     const bool staged = bx0 >= 0 && bx1 < sw && by0 >= 0 && by1 < sh - 1 && nrows <= WT_ROWS && (bx1 - bx0 + 1) + 15 <= WT_STRIDE &&
-                        (nrows - 1) * WT_STRIDE + 16 * ((c0 + (nrows - 1) * pm) >> 4) + WT_STRIDE <= stage_bytes;
+                        fits(bstride);
     __syncwarp();
     if (staged) {
       // item = (row, 16-byte chunk); all loads first, then the stores
@@ -714,7 +734,7 @@ __device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ d
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int item = lane + 32 * i, row = item >> 2, k = item & 3;
-        if (row < nrows) *reinterpret_cast<uint4*>(stage + row * WT_STRIDE + 16 * ((c0 + row * pm) >> 4) + 16 * k) = v[i];
+        if (row < nrows) *reinterpret_cast<uint4*>(stage + row * bstride + 16 * ((c0 + row * pm) >> 4) + 16 * k) = v[i];
       }
       __syncwarp();
       int X0l, Y0l;                      // lane yy holds the row origin of tile row yy
