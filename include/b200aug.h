@@ -41,7 +41,7 @@ extern "C" {
 /* per-sample status codes written to status_out */
 #define B200AUG_S_OK 0
 #define B200AUG_S_EMPTY_BOX 1     /* view box with non-positive width/height (cv2.resize would throw) */
-#define B200AUG_S_UNSUPPORTED 2   /* INTER_AREA with one axis up-scaling (unreachable from GeneralFocusRoi) */
+#define B200AUG_S_UNSUPPORTED 2   /* reserved (INTER_AREA with an up-scaling axis is handled since ABI 4: cv2's 2-tap area-mode path) */
 #define B200AUG_S_ROWBUF 3        /* reserved (ABI 1 reported row-buffer overflow; since ABI 2 such samples take the per-pixel path) */
 
 /* field categories: FieldCategory, trackertraincode/datasets/dshdf5pose.py:21-28 */

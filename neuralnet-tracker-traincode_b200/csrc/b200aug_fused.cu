@@ -66,6 +66,7 @@ struct Plan {
   int do_flip, rot_dir;
   int status;
   int kx;              // widest horizontal INTER_AREA tap count (filled while the tables are built)
+  int lin_area;        // RS_LINEAR with cv2's INTER_AREA coefficient rule (INTER_AREA requested while an axis up-scales)
   int fin;             // final rounding of the area sum: 0 rint | 1 integer 2x2 (sum + 2) >> 2 | 2 rint(sum * inv_area)
   int has_t2;
   AffDerived t1, t2, t3;           // label transforms in pipeline order (the half-pixel offset is a constant)
@@ -328,6 +329,7 @@ __device__ void plan_resize(const B200AugFusedArgs& a, const PlanCore& c, Plan& 
   const int ow = a.out_w, oh = a.out_h;
   P.status = B200AUG_S_OK;
   P.fin = 0;
+  P.lin_area = 0;
   if (c.cw <= 0 || c.ch <= 0) {
     P.status = B200AUG_S_EMPTY_BOX;
     P.rs_mode = RS_COPY;
@@ -346,8 +348,12 @@ __device__ void plan_resize(const B200AugFusedArgs& a, const PlanCore& c, Plan& 
         P.inv_area = (float)(1.0 / (double)(P.iscale_x * P.iscale_y));
         if (fast) P.fin = (P.iscale_x == 2 && P.iscale_y == 2) ? 1 : 2;
       } else {
-        P.status = B200AUG_S_UNSUPPORTED;
-        P.rs_mode = RS_COPY;
+        // cv::resize(INTER_AREA) with an up-scaling axis: not the area kernel but the 2-tap linear one, with the
+        // "area mode" coefficient rule on BOTH axes (imgproc/resize.cpp; checked bit-exact against cv2 4.13 for mixed and
+        // pure up-scaling).  Reachable with non-square outputs (the localizer's 288 x 224: view side between 224 and 288);
+        // a square output never gets here, the rounded view box is at most one pixel off square.
+        P.rs_mode = RS_LINEAR;
+        P.lin_area = 1;
       }
     } else {
       P.rs_mode = RS_LINEAR;
@@ -537,10 +543,19 @@ __device__ void area_tab_entry(int d, double scale, int ssize, int& start, int& 
 }
 
 // cv::resize INTER_LINEAR taps (oracle/cv2_model.py:linear_tab + border rules)
-__device__ void linear_tab_entry(int d, double scale, int ssize, bool is_x, int& i0, int& i1, int& w0, int& w1) {
-  float f = (float)((d + 0.5) * scale - 0.5);
-  int s = (int)floorf(f);
-  f = __fsub_rn(f, (float)s);
+__device__ void linear_tab_entry(int d, double scale, int ssize, int dsize, bool area_mode, bool is_x, int& i0, int& i1, int& w0, int& w1) {
+  float f;
+  int s;
+  if (!area_mode) {
+    f = (float)((d + 0.5) * scale - 0.5);
+    s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+  } else {  // INTER_AREA asked for, an axis up-scales: sx = floor(dx * scale), fx = (dx + 1) - (sx + 1) * inv_scale, wrapped into [0, 1)
+    const double inv_scale = (double)dsize / (double)ssize;
+    s = (int)floor(d * scale);
+    f = (float)((double)(d + 1) - (double)(s + 1) * inv_scale);
+    f = (f <= 0.f) ? 0.f : __fsub_rn(f, floorf(f));
+  }
   if (is_x) {
     if (s < 0) { s = 0; f = 0.f; }
     if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
@@ -1303,7 +1318,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
         if (is_x) atomicMax(&P.kx, nf & 0xffff);
       } else {
         int i0, i1, w0, w1;
-        linear_tab_entry(d, sc, ss, is_x, i0, i1, w0, w1);
+        linear_tab_entry(d, sc, ss, is_x ? ow : oh, P.lin_area != 0, is_x, i0, i1, w0, w1);
         T.start[i] = i0; T.n[i] = i1; T.a[i] = __int_as_float(w0); T.b[i] = __int_as_float(w1);
       }
     };

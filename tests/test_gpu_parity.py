@@ -282,6 +282,34 @@ def test_nonsquare_output_localizer_shape(dtr):
         assert_labels(r.batch["pt3d_68"][i], s.data["pt3d_68"], "pt3d_68", atol=2e-4)
 
 
+def test_inter_area_with_an_upscaling_axis(dtr):
+    """The reference asks cv2.resize for INTER_AREA whenever the mean scale is < 1 (image_geometric_cv2.py:65-82); when one
+    axis up-scales cv2 then runs its 2-tap kernel with the area-mode coefficient rule on both axes.  Non-square outputs
+    (view side between the output height and width: the localizer's 288 x 224) hit this; square outputs cannot, the rounded
+    view box is at most one pixel off square."""
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datatransformation import _engine as E
+
+    sides = [262.0, 270.0, 275.0, 281.0, 286.0, 225.0, 240.0]
+    cs, rng = random_inputs(len(sides), 33, wh=(640, 480))
+    for c, side in zip(cs, sides):
+        cx, cy = rng.uniform(250, 390), rng.uniform(200, 280)
+        c["roi"] = np.array([cx - 100, cy - 100, cx + 100, cy + 100], np.float32)
+    scales = torch.tensor([s / 200.0 for s in sides])
+    geo = E.GeoParams(scales, torch.zeros(len(sides)), torch.zeros(len(sides), 2))
+    r = E.fused_forward(make_batch(cs), flags=N.F_FOCUS, out_size=(288, 224), geo=geo, want_view_roi=True, want_status=True)
+    assert not r.status.cpu().numpy().any()
+    img = r.batch["image"].cpu().numpy()[:, 0]
+    mixed = 0
+    for i, c in enumerate(cs):
+        s, inter = ogeo.focus_roi(to_sample(c), ogeo.RoiFocusParams(np.float32(scales[i].item()), 0.0, (0.0, 0.0)), (288, 224))
+        v = inter["view_roi"]
+        mixed += (v[2] - v[0] < 288) and (0.5 * (288 / (v[2] - v[0]) + 224 / (v[3] - v[1])) < 1.0)
+        assert np.array_equal(r.view_roi.cpu().numpy()[i], v)
+        assert np.array_equal(img[i], s.data["image"][0]), f"sample {i} (view box {v})"
+    assert mixed >= 4
+
+
 def test_integer_factor_and_frame_borders(dtr):
     """Exact 2x / 3x INTER_AREA (cv2's integer box path), crops crossing every frame border, with and without rotation."""
     from trackertraincode_b200 import _native as N
