@@ -429,7 +429,7 @@ def run_gpu_arm(args):
                     "zero_copy_frames": {"value": e2e_zero_copy, "h2d_bytes_per_step": label_bytes + int(alg_bytes - BATCH * (OUT * OUT * 4 + LABEL_BYTES)),
                                          "note": "frames left in pinned host memory and read in place by the kernel (only the view "
                                                  "boxes cross PCIe), synchronised every step"}},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,  # plan_kernel + fused_augment_kernel per step
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "fused_augment_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_us": kernel_s * 1e6, "peak_source": peak_src},

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200AUG_ABI_VERSION 4
+#define B200AUG_ABI_VERSION 5
 
 /* error codes */
 #define B200AUG_OK 0
@@ -157,6 +157,12 @@ typedef struct B200AugFusedArgs {
    * i.e. in L2.  Without it (NULL) or when a canvas does not fit, canvas rows are produced one at a time instead. */
   uint8_t* workspace;
   int64_t workspace_stride;
+  /* optional scratch for the plans: B records of plan_stride bytes (>= b200aug_plan_stride(out_w, out_h), a multiple of
+   * 16).  When given (and an image is produced) a small kernel computes every sample's plan and cv2 resize tables first
+   * and the fused kernel loads them, instead of every CTA building them behind its full register / shared-memory
+   * footprint.  NULL = build them inside the fused kernel. */
+  uint8_t* plans;
+  int64_t plan_stride;
 
   B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
 } B200AugFusedArgs;
@@ -169,6 +175,8 @@ int b200aug_last_cuda_error(void);
 size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capacity);
 /* bytes of scratch per sample that hold the rotated canvas of a crop box of up to max_side x max_side source pixels */
 int64_t b200aug_workspace_stride(int max_side);
+/* bytes of one record of B200AugFusedArgs::plans for this output size */
+int64_t b200aug_plan_stride(int out_w, int out_h);
 
 /* Host -> device upload of the rows the fused kernel will read, instead of whole frames (Batch.to(device),
  * datasets/batch.py:161-165 / pipelines.py:508): for each of `batch` stacked frames (host_frames: PINNED host memory,

@@ -1130,72 +1130,10 @@ __device__ __noinline__ float blurred_value(const uint8_t* tile, const float* lu
   return acc;
 }
 
-// ------------------------------------------------------------------------------------------------ the kernel
-
-__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap, int lay_w, int lay_h) {
-  const B200AugFusedArgs& a = K.a;
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t cr_u, cl_u;
-  cluster_info(cr_u, cl_u);
-  const int cr = (int)cr_u, cl = (int)cl_u;  // rank in / size of the cluster that shares this sample
-  // launch order -> sample: the caller may schedule expensive samples (rotated, blurred) first so that the cheap ones
-  // fill the tail of the grid
-  const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4: checked at launch), divisions become shifts
-  const int b = a.order ? a.order[blockIdx.x >> cs] : (int)(blockIdx.x >> cs);
-  const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // (lay_w, lay_h) = (out_w, out_h) when an image is produced; label-only launches use a 1 x 1 layout so that label
-  // frames of any size (normalize_batch on 640 x 480 labels) never hit the shared-memory budget
-  const SmemLayout L = smem_layout(lay_w, lay_h, cap);
-  Plan& P = *reinterpret_cast<Plan*>(smem);
-  float* lut = reinterpret_cast<float*>(smem + ((sizeof(Plan) + 15) & ~size_t(15)));
-  float* eq_lut = lut + 256;
-  unsigned* hist8 = reinterpret_cast<unsigned*>(eq_lut + 256);
-  unsigned* binhist = hist8 + 256;
-  Tabs T;
-  T.start = reinterpret_cast<int*>(smem + L.off_tabs);
-  T.n = T.start + L.ntab;
-  T.a = reinterpret_cast<float*>(T.n + L.ntab);
-  T.b = T.a + L.ntab;
-  T.c = T.b + L.ntab;
-  uint8_t* tile = smem + L.off_tile;
-  uint8_t* rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
-  int2* dtab = reinterpret_cast<int2*>(smem + L.off_dtab);
-  float* lab = reinterpret_cast<float*>(smem + L.off_lab);
-  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // cluster exchange barrier
-
-  trace_mark(a, 0);
-  if (a.trace_out && tid == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    a.trace_out[(size_t)blockIdx.x * 16 + 5] = smid;
-  }
-  if (tid == 0) {
-    mbar_init(xbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // ---- label data of this sample -> shared memory (overlaps the plan; labels do not depend on it) ----------
-  int lab_total = 0;
-  for (int f = 0; f < a.n_fields; ++f) {
-    const B200AugField& F = a.fields[f];
-    if (F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4) lab_total += F.count * F.dim;
-  }
-  const bool lab_staged = lab_total <= LAB_CAP;
-  if (lab_staged) {
-    int off = 0;
-    for (int f = 0; f < a.n_fields; ++f) {
-      const B200AugField& F = a.fields[f];
-      if (!(F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4)) continue;
-      const int n = F.count * F.dim;
-      const float* src = F.in + (size_t)b * n;
-      for (int i = tid; i < n; i += NTHREADS)  // asynchronous: the loads overlap the plan instead of stalling in front of it
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(lab + off + i)), "l"(src + i) : "memory");
-      off += n;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // ---- prologue: the plan, one branch per warp (see plan_core) --------------------------------------------
-  {
+// The plan of one sample, one branch per warp (see plan_core); also writes the per-sample side outputs (view box, focus
+// transform, back-transform, the roi regenerated from landmarks).  Runs either in plan_kernel (ahead of the fused kernel, so
+// that its latency chains do not occupy a big CTA slot) or at the top of the fused kernel itself.
+__device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, int warp, int lane, int cr) {
     float box[4] = {0.f, 0.f, 0.f, 0.f};
     const bool lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && a.landmark_field >= 0;
     const bool half = a.flags & B200AUG_F_HALF_PIXEL;
@@ -1261,42 +1199,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       default: break;
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the staged labels
-  __syncthreads();
 
-  trace_mark(a, 1);
-  // Samples whose photometric chain is a single point function (no equalize, blur or noise: more than half of the training
-  // draws, and every evaluation sample) get their LUT now: the INTER_AREA pass can then write float32 output directly
-  // (`direct` below).  The cluster barrier in front of the resampling orders these writes before their first use.
-  const bool lut_early = (a.flags & B200AUG_F_NORMALIZE) && a.image_f32_out && P.blur_pos < 0 && P.eq_pos < 0 && !P.any_noise;
-  if (lut_early) {
-    float xv = apply_point_ops(P, __fmul_rn((float)tid, 0.00390625f), 0, P.n_ops, eq_lut);
-    if ((a.flags & B200AUG_F_PHOTOMETRIC) && a.photo.clip) xv = fminf(fmaxf(xv, 0.f), 1.f);
-    if (a.flags & B200AUG_F_WHITEN) xv = __fsub_rn(xv, 0.5f);
-    lut[tid] = xv;
-  }
-  // this CTA's band of output rows, and the bytes the other CTAs of the cluster will bulk-copy into this tile
-  const int rows_lo = (cr * oh) >> cs, rows_hi = ((cr + 1) * oh) >> cs;
-  int rx_bytes = 0;
-  if (cl > 1 && P.status == B200AUG_S_OK && P.rot_dir == 0) {
-    for (int q = 0; q < cl; ++q) {
-      if (q == cr) continue;
-      const int lo = ((q * oh) >> cs) * ow, hi = (((q + 1) * oh) >> cs) * ow, alo = min((lo + 15) & ~15, hi), ahi = max(hi & ~15, alo);
-      rx_bytes += ahi - alo;
-    }
-    if (tid == 0 && rx_bytes)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(xbar)), "r"(rx_bytes) : "memory");
-  }
-  if (tid == 0 && a.status_out) a.status_out[b] = P.status;
-  // The labels only need the plan; they are transformed once the CTAs of the cluster no longer wait for each other (after the
-  // tile exchange), so that rank 0 does not hold its partner up in front of the resampling.
-  const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
-  if (!want_image) {
-    if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
-    return;
-  }
-
-  // ---- resize tables, warp column tables ------------------------------------------------------------------
+// cv2's per-axis resize tables of one sample (x entries first, then y), and Plan::kx
+__device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P, const Tabs& T, int tid, int lane) {
+  const int ow = a.out_w, oh = a.out_h;
   const int rs = P.rs_mode;
   if (rs == RS_AREA || rs == RS_LINEAR || rs == RS_AREA_INT) {
     // two independent entries per thread and iteration: 129 + 129 entries on 256 threads would otherwise pay a second,
@@ -1343,6 +1249,154 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       for (int i = tid; i < ntab; i += NTHREADS) tab_entry(i);
     }
   }
+}
+
+// bytes of one sample's record in B200AugFusedArgs::plans: the Plan, then the tables of out_w + out_h entries
+__host__ __device__ inline size_t plan_bytes() { return (sizeof(Plan) + 15) & ~size_t(15); }
+__host__ __device__ inline size_t plan_tab_bytes(int ow, int oh) { return ((size_t)(ow + oh) * 5 * 4 + 15) & ~size_t(15); }
+
+// Plans + tables of all samples, one CTA per sample, ahead of the fused kernel (B200AugFusedArgs::plans).
+__global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ KArgs K) {
+  const B200AugFusedArgs& a = K.a;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntab = a.out_w + a.out_h;
+  Plan& P = *reinterpret_cast<Plan*>(smem);
+  Tabs T;
+  T.start = reinterpret_cast<int*>(smem + plan_bytes());
+  T.n = T.start + ntab;
+  T.a = reinterpret_cast<float*>(T.n + ntab);
+  T.b = T.a + ntab;
+  T.c = T.b + ntab;
+  // programmatic dependent launch: the fused kernel may be scheduled now; it waits (griddepcontrol.wait) for this whole grid
+  // to complete and flush before it reads the plans
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  build_plan(a, b, P, warp, lane, 0);
+  __syncthreads();
+  build_tables(a, P, T, tid, lane);
+  __syncthreads();
+  const int nvec = (int)((plan_bytes() + plan_tab_bytes(a.out_w, a.out_h)) >> 4);
+  uint4* dst = reinterpret_cast<uint4*>(a.plans + (size_t)b * a.plan_stride);
+  const uint4* src = reinterpret_cast<const uint4*>(smem);
+  for (int i = tid; i < nvec; i += NTHREADS) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+
+__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap, int lay_w, int lay_h) {
+  const B200AugFusedArgs& a = K.a;
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t cr_u, cl_u;
+  cluster_info(cr_u, cl_u);
+  const int cr = (int)cr_u, cl = (int)cl_u;  // rank in / size of the cluster that shares this sample
+  // launch order -> sample: the caller may schedule expensive samples (rotated, blurred) first so that the cheap ones
+  // fill the tail of the grid
+  const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4: checked at launch), divisions become shifts
+  const int b = a.order ? a.order[blockIdx.x >> cs] : (int)(blockIdx.x >> cs);
+  const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (lay_w, lay_h) = (out_w, out_h) when an image is produced; label-only launches use a 1 x 1 layout so that label
+  // frames of any size (normalize_batch on 640 x 480 labels) never hit the shared-memory budget
+  const SmemLayout L = smem_layout(lay_w, lay_h, cap);
+  Plan& P = *reinterpret_cast<Plan*>(smem);
+  float* lut = reinterpret_cast<float*>(smem + ((sizeof(Plan) + 15) & ~size_t(15)));
+  float* eq_lut = lut + 256;
+  unsigned* hist8 = reinterpret_cast<unsigned*>(eq_lut + 256);
+  unsigned* binhist = hist8 + 256;
+  Tabs T;
+  T.start = reinterpret_cast<int*>(smem + L.off_tabs);
+  T.n = T.start + L.ntab;
+  T.a = reinterpret_cast<float*>(T.n + L.ntab);
+  T.b = T.a + L.ntab;
+  T.c = T.b + L.ntab;
+  uint8_t* tile = smem + L.off_tile;
+  uint8_t* rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
+  int2* dtab = reinterpret_cast<int2*>(smem + L.off_dtab);
+  float* lab = reinterpret_cast<float*>(smem + L.off_lab);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // cluster exchange barrier
+
+  trace_mark(a, 0);
+  if (a.trace_out && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace_out[(size_t)blockIdx.x * 16 + 5] = smid;
+  }
+  if (tid == 0) {
+    mbar_init(xbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- label data of this sample -> shared memory (overlaps the plan; labels do not depend on it) ----------
+  int lab_total = 0;
+  for (int f = 0; f < a.n_fields; ++f) {
+    const B200AugField& F = a.fields[f];
+    if (F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4) lab_total += F.count * F.dim;
+  }
+  const bool lab_staged = lab_total <= LAB_CAP;
+  if (lab_staged) {
+    int off = 0;
+    for (int f = 0; f < a.n_fields; ++f) {
+      const B200AugField& F = a.fields[f];
+      if (!(F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4)) continue;
+      const int n = F.count * F.dim;
+      const float* src = F.in + (size_t)b * n;
+      for (int i = tid; i < n; i += NTHREADS)  // asynchronous: the loads overlap the plan instead of stalling in front of it
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(lab + off + i)), "l"(src + i) : "memory");
+      off += n;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // ---- the plan: precomputed by plan_kernel (loaded with the staged labels' cp.async group) or built here -----------
+  const bool preplanned = a.plans != nullptr && lay_w == ow && lay_h == oh;
+  if (preplanned) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // plan_kernel (launched just before, overlapping our start) is done
+    const unsigned char* rec = a.plans + (size_t)b * a.plan_stride;
+    const int nv_plan = (int)(plan_bytes() >> 4), nv_tab = (int)(plan_tab_bytes(ow, oh) >> 4);
+    for (int i = tid; i < nv_plan + nv_tab; i += NTHREADS) {
+      const uint32_t d = (i < nv_plan) ? smem_u32(smem) + 16u * i : smem_u32(smem + L.off_tabs) + 16u * (i - nv_plan);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(rec + 16 * (size_t)i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    build_plan(a, b, P, warp, lane, cr);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the staged labels
+  __syncthreads();
+
+  trace_mark(a, 1);
+  // Samples whose photometric chain is a single point function (no equalize, blur or noise: more than half of the training
+  // draws, and every evaluation sample) get their LUT now: the INTER_AREA pass can then write float32 output directly
+  // (`direct` below).  The cluster barrier in front of the resampling orders these writes before their first use.
+  const bool lut_early = (a.flags & B200AUG_F_NORMALIZE) && a.image_f32_out && P.blur_pos < 0 && P.eq_pos < 0 && !P.any_noise;
+  if (lut_early) {
+    float xv = apply_point_ops(P, __fmul_rn((float)tid, 0.00390625f), 0, P.n_ops, eq_lut);
+    if ((a.flags & B200AUG_F_PHOTOMETRIC) && a.photo.clip) xv = fminf(fmaxf(xv, 0.f), 1.f);
+    if (a.flags & B200AUG_F_WHITEN) xv = __fsub_rn(xv, 0.5f);
+    lut[tid] = xv;
+  }
+  // this CTA's band of output rows, and the bytes the other CTAs of the cluster will bulk-copy into this tile
+  const int rows_lo = (cr * oh) >> cs, rows_hi = ((cr + 1) * oh) >> cs;
+  int rx_bytes = 0;
+  if (cl > 1 && P.status == B200AUG_S_OK && P.rot_dir == 0) {
+    for (int q = 0; q < cl; ++q) {
+      if (q == cr) continue;
+      const int lo = ((q * oh) >> cs) * ow, hi = (((q + 1) * oh) >> cs) * ow, alo = min((lo + 15) & ~15, hi), ahi = max(hi & ~15, alo);
+      rx_bytes += ahi - alo;
+    }
+    if (tid == 0 && rx_bytes)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(xbar)), "r"(rx_bytes) : "memory");
+  }
+  if (tid == 0 && a.status_out) a.status_out[b] = P.status;
+  // The labels only need the plan; they are transformed once the CTAs of the cluster no longer wait for each other (after the
+  // tile exchange), so that rank 0 does not hold its partner up in front of the resampling.
+  const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
+  if (!want_image) {
+    if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
+    return;
+  }
+
+  // ---- resize tables (unless they came with the precomputed plan), warp column tables ---------------------------------
+  const int rs = P.rs_mode;
+  if (!preplanned) build_tables(a, P, T, tid, lane);
   trace_mark(a, 8);
   const bool use_dtab = (P.src_mode == SRC_WARP) && (P.cw <= DT_CAP);
   if (use_dtab) {
@@ -2002,6 +2056,11 @@ extern "C" size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capa
   return t <= 227 * 1024 ? t : 0;
 }
 
+extern "C" int64_t b200aug_plan_stride(int out_w, int out_h) {
+  if (out_w <= 0 || out_h <= 0) return 0;
+  return (int64_t)(plan_bytes() + plan_tab_bytes(out_w, out_h));
+}
+
 extern "C" int64_t b200aug_workspace_stride(int max_side) {
   if (max_side <= 0) return 0;
   const int64_t spitch = (max_side + 16 + 15) & ~15;
@@ -2094,18 +2153,36 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   K.a = a;
   int cl = a.cluster_size > 0 ? a.cluster_size : DEFAULT_CLUSTER;
   if (cl != 1 && cl != 2 && cl != 4) return B200AUG_E_INVALID_ARG;
+  if (a.plans && want_image) {
+    const size_t rec = plan_bytes() + plan_tab_bytes(a.out_w, a.out_h);
+    if (a.plan_stride < (int64_t)rec || (a.plan_stride & 15) || (reinterpret_cast<uintptr_t>(a.plans) & 15)) return B200AUG_E_INVALID_ARG;
+    if (rec > 48 * 1024) {
+      K.a.plans = nullptr;  // (very large outputs: the tables are built inside the fused kernel)
+    } else {
+      plan_kernel<<<a.batch, NTHREADS, rec, (cudaStream_t)stream>>>(K);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+    }
+  } else {
+    K.a.plans = nullptr;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)a.batch * cl);
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (K.a.plans) {  // start while plan_kernel drains (the kernel waits with griddepcontrol.wait before reading the plans)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   e = cudaLaunchKernelEx(&cfg, fused_augment_kernel, K, cap, lay_w, lay_h);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }

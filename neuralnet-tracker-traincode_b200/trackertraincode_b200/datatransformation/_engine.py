@@ -182,6 +182,20 @@ def _workspace(device, B: int):
     return ws, stride
 
 
+_PLAN_BUFFERS: Dict[Any, torch.Tensor] = {}
+
+
+def _plan_buffer(device, B: int, ow: int, oh: int):
+    """Scratch for the plans + resize tables of one launch (B200AugFusedArgs.plans), cached like the canvas workspace."""
+    stride = int(N.lib.b200aug_plan_stride(ow, oh))
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _PLAN_BUFFERS.get(key)
+    if buf is None or buf.numel() < B * stride:
+        buf = torch.empty(B * stride, dtype=torch.uint8, device=device)
+        _PLAN_BUFFERS[key] = buf
+    return buf, stride
+
+
 def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams]) -> Optional[torch.Tensor]:
     """Most expensive samples first (B200AugFusedArgs.order).  Only parameters that are still on the host are looked at
     -- this never synchronises with the device; returns None when nothing distinguishes the samples."""
@@ -236,7 +250,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
                   want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0,
-                  schedule: bool = True) -> PreparedCall:
+                  schedule: bool = True, preplan: bool = True) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -364,6 +378,10 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         ws, stride = _workspace(device, B)
         args.workspace, args.workspace_stride = ws.data_ptr(), stride
         keep.append(ws)
+    if image_keys and preplan:
+        pb, pstride = _plan_buffer(device, B, ow, oh)
+        args.plans, args.plan_stride = pb.data_ptr(), pstride
+        keep.append(pb)
     if flags & N.F_FOCUS:
         if want_view_roi:
             view_roi = torch.empty((B, 4), dtype=torch.int32, device=device)
