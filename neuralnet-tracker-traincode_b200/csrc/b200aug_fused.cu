@@ -1133,7 +1133,7 @@ __device__ __noinline__ float blurred_value(const uint8_t* tile, const float* lu
 // The plan of one sample, one branch per warp (see plan_core); also writes the per-sample side outputs (view box, focus
 // transform, back-transform, the roi regenerated from landmarks).  Runs either in plan_kernel (ahead of the fused kernel, so
 // that its latency chains do not occupy a big CTA slot) or at the top of the fused kernel itself.
-__device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, int warp, int lane, int cr) {
+__device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, int warp, int lane, int cr, PlanCore* shared_core) {
     float box[4] = {0.f, 0.f, 0.f, 0.f};
     const bool lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && a.landmark_field >= 0;
     const bool half = a.flags & B200AUG_F_HALF_PIXEL;
@@ -1144,7 +1144,14 @@ __device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Pla
       const float* r = a.fields[a.roi_field].in + 4 * (size_t)b;
       box[0] = r[0]; box[1] = r[1]; box[2] = r[2]; box[3] = r[3];
     }
-    const PlanCore c = plan_core(a, b, box);
+    // the common chain (view box -> focus transform) once, by warp 0, handed to the branch warps through shared memory:
+    // evaluating it redundantly in every warp saved a barrier but cost 7/8 of this function's issue slots
+    if (warp == 0) {
+      const PlanCore c0 = plan_core(a, b, box);
+      if (lane == 0) *shared_core = c0;
+    }
+    __syncthreads();
+    const PlanCore c = *shared_core;
     const bool focus = a.flags & B200AUG_F_FOCUS;
     switch (warp) {
       case 0:
@@ -1271,7 +1278,7 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
   // programmatic dependent launch: the fused kernel may be scheduled now; it waits (griddepcontrol.wait) for this whole grid
   // to complete and flush before it reads the plans
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  build_plan(a, b, P, warp, lane, 0);
+  build_plan(a, b, P, warp, lane, 0, reinterpret_cast<PlanCore*>(smem + plan_bytes() + plan_tab_bytes(a.out_w, a.out_h)));
   __syncthreads();
   build_tables(a, P, T, tid, lane);
   __syncthreads();
@@ -1357,7 +1364,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   } else {
-    build_plan(a, b, P, warp, lane, cr);
+    build_plan(a, b, P, warp, lane, cr, reinterpret_cast<PlanCore*>(lut));  // (the LUT area is idle until the plan exists)
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the staged labels
   __syncthreads();
@@ -2159,7 +2166,7 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
     if (rec > 48 * 1024) {
       K.a.plans = nullptr;  // (very large outputs: the tables are built inside the fused kernel)
     } else {
-      plan_kernel<<<a.batch, NTHREADS, rec, (cudaStream_t)stream>>>(K);
+      plan_kernel<<<a.batch, NTHREADS, rec + ((sizeof(PlanCore) + 15) & ~size_t(15)), (cudaStream_t)stream>>>(K);
       e = cudaGetLastError();
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
     }
