@@ -166,7 +166,6 @@ __device__ __forceinline__ void trace_mark(const B200AugFusedArgs& a, int slot) 
 
 // ---- thread-block clusters: the CTAs of a cluster share one sample (each resamples a band of rows and stores the
 // pixels into every CTA's tile through distributed shared memory, then each finishes its share of the output)
-constexpr int MAX_CLUSTER = 4;
 
 __device__ __forceinline__ void cluster_info(uint32_t& rank, uint32_t& size) {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
