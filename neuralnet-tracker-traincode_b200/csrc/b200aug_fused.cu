@@ -1512,8 +1512,30 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
         tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
       }
     }
+  } else if (P.status == B200AUG_S_OK && rs == RS_LINEAR && P.src_mode != SRC_WARP) {
+    // cv2's 2-tap kernels (INTER_LINEAR up-scaling, or INTER_AREA with an up-scaling axis) from a crop: scalar_out_px()
+    // specialised -- plan fields in registers, no resampler / source dispatch per tap; consecutive threads = consecutive
+    // output columns, so the taps of a warp fall into a few cache lines
+    const uint8_t* const src = P.src;
+    const int pitch = P.pitch, sw = P.sw, sh = P.sh, x0 = P.x0, y0 = P.y0;
+    for (int p = rows_lo * ow + tid; p < rows_hi * ow; p += NTHREADS) {
+      const int dy = p / ow, dx = p - dy * ow;
+      const int sxa = x0 + T.start[dx], sxb = x0 + T.n[dx], sya = y0 + T.start[ow + dy], syb = y0 + T.n[ow + dy];
+      const int a0 = __float_as_int(T.a[dx]), a1 = __float_as_int(T.b[dx]);
+      const int b0 = __float_as_int(T.a[ow + dy]), b1 = __float_as_int(T.b[ow + dy]);
+      const bool xa = (unsigned)sxa < (unsigned)sw, xb = (unsigned)sxb < (unsigned)sw;
+      const bool ya = (unsigned)sya < (unsigned)sh, yb = (unsigned)syb < (unsigned)sh;
+      const uint8_t* ra = src + (ptrdiff_t)sya * pitch;
+      const uint8_t* rb = src + (ptrdiff_t)syb * pitch;
+      // (coherent loads: the source may be the scratch canvas written earlier in this kernel)
+      const int p00 = (ya && xa) ? ra[sxa] : 0, p01 = (ya && xb) ? ra[sxb] : 0;
+      const int p10 = (yb && xa) ? rb[sxa] : 0, p11 = (yb && xb) ? rb[sxb] : 0;
+      const int h0 = p00 * a0 + p01 * a1, h1 = p10 * a0 + p11 * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      tile[tm.o + dy * tm.sa + dx * tm.sb] = (uint8_t)min(max(v, 0), 255);
+    }
   } else if (P.status == B200AUG_S_OK) {
-    // per-pixel path: integer-factor area, linear up-scaling, plain copy, very wide taps / canvases
+    // per-pixel path: integer-factor area, plain copy, very wide taps / canvases, rotated samples without a scratch canvas
     for (int p = rows_lo * ow + tid; p < rows_hi * ow; p += NTHREADS) {
       const int dy = p / ow, dx = p - dy * ow;
       tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
