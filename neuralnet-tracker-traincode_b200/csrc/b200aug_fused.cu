@@ -1709,17 +1709,30 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       for (int ry0 = p_lo / ow; ry0 <= y_last; ry0 += strip) {
         const int ry1 = min(ry0 + strip - 1, y_last), nr = ry1 - ry0 + 5;
         __syncthreads();  // the previous strip's vertical pass is done with hb
-        for (int v = tid; v < nr * ow; v += NTHREADS) {
-          const int rr = v / ow, x = v - rr * ow;
-          const uint8_t* row = tile + reflect_idx(ry0 - 2 + rr, oh) * ow;
-          float t = __fmul_rn(g0, lut[row[reflect_idx(x - 2, ow)]]);
-          t = __fadd_rn(t, __fmul_rn(g1, lut[row[reflect_idx(x - 1, ow)]]));
-          t = __fadd_rn(t, __fmul_rn(g2, lut[row[x]]));
-          t = __fadd_rn(t, __fmul_rn(g1, lut[row[reflect_idx(x + 1, ow)]]));
-          t = __fadd_rn(t, __fmul_rn(g0, lut[row[reflect_idx(x + 2, ow)]]));
-          hb[v] = t;
+        // horizontal pass over the strip's rows (incl. halo), one value per thread and step; (row, column) advance without
+        // a division, interior columns need no reflection
+        {
+          const int step_r = NTHREADS / ow, step_x = NTHREADS - step_r * ow;
+          int rr = tid / ow, x = tid - rr * ow;
+          for (int v = tid; v < nr * ow; v += NTHREADS) {
+            const uint8_t* row = tile + reflect_idx(ry0 - 2 + rr, oh) * ow;
+            const bool inner = x >= 2 && x + 2 < ow;
+            const int xm2 = inner ? x - 2 : reflect_idx(x - 2, ow), xm1 = inner ? x - 1 : reflect_idx(x - 1, ow);
+            const int xp1 = inner ? x + 1 : reflect_idx(x + 1, ow), xp2 = inner ? x + 2 : reflect_idx(x + 2, ow);
+            float t = __fmul_rn(g0, lut[row[xm2]]);
+            t = __fadd_rn(t, __fmul_rn(g1, lut[row[xm1]]));
+            t = __fadd_rn(t, __fmul_rn(g2, lut[row[x]]));
+            t = __fadd_rn(t, __fmul_rn(g1, lut[row[xp1]]));
+            t = __fadd_rn(t, __fmul_rn(g0, lut[row[xp2]]));
+            hb[v] = t;
+            x += step_x;
+            rr += step_r;
+            if (x >= ow) { x -= ow; ++rr; }
+          }
         }
         __syncthreads();
+        // vertical pass + the ops behind the blur; only the pixels of [p_lo, p_hi) are this CTA's
+        const bool post_ops = P.blur_pos + 1 < P.n_ops;
         const int q_lo = max(p_lo, ry0 * ow), q_hi = min(p_hi, (ry1 + 1) * ow);
         for (int p = q_lo + tid; p < q_hi; p += NTHREADS) {
           const float* c = hb + (p - ry0 * ow);  // horizontal-pass value of the pixel two rows up
@@ -1728,7 +1741,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
           acc = __fadd_rn(acc, __fmul_rn(g2, c[2 * ow]));
           acc = __fadd_rn(acc, __fmul_rn(g1, c[3 * ow]));
           acc = __fadd_rn(acc, __fmul_rn(g0, c[4 * ow]));
-          out[p] = apply_point_ops(P, acc, P.blur_pos + 1, P.n_ops, eq_lut);
+          out[p] = post_ops ? apply_point_ops(P, acc, P.blur_pos + 1, P.n_ops, eq_lut) : acc;
         }
       }
     }
