@@ -146,10 +146,11 @@ def test_launch_order_puts_heavy_samples_first():
     assert sorted(o.tolist()) == list(range(B)) and set(o[:2].tolist()) == {1, 6}
     ph = draw_photo_params(B, 0, 0)
     ph.order, ph.apply = [5, 0, 2, 3], torch.zeros(B, 6, dtype=torch.bool)
-    ph.apply[3, 5] = True  # blurred sample: the most expensive of all
+    ph.apply[3, 5] = True  # blurred: dearer than a plain crop, cheaper than a rotated one
+    ph.apply[6, 5] = True  # rotated and blurred: the most expensive of all
     ph.noise_apply = torch.zeros(B, 4, dtype=torch.bool)
     o = E.launch_order(B, geo, ph)
-    assert o[0] == 3 and set(o[1:3].tolist()) == {1, 6}
+    assert o[:3].tolist() == [6, 1, 3]
 
 
 class _DS(torch.utils.data.Dataset):
