@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200AUG_ABI_VERSION 5
+#define B200AUG_ABI_VERSION 6
 
 /* error codes */
 #define B200AUG_OK 0
@@ -59,6 +59,11 @@ extern "C" {
 #define B200AUG_F_NORMALIZE 0x10u          /* normalize_batch                   batch/normalization.py:20-56 */
 #define B200AUG_F_PHOTOMETRIC 0x20u        /* KorniaImageDistortions x2         batch/intensity.py:30-64, pipelines.py:508-527 */
 #define B200AUG_F_WHITEN 0x40u             /* whiten_batch                      batch/normalization.py:94-99 */
+
+/* B200AugFusedArgs::phase */
+#define B200AUG_PHASE_ALL 0
+#define B200AUG_PHASE_PLAN 1
+#define B200AUG_PHASE_MAIN 2
 
 #define B200AUG_MAX_FIELDS 8
 #define B200AUG_NUM_OPS 6
@@ -114,7 +119,7 @@ typedef struct B200AugFusedArgs {
   int32_t batch;
   int32_t out_w, out_h;         /* crop size (129 x 129 for the pose net) */
   uint32_t flags;               /* B200AUG_F_* */
-  int32_t rowbuf_capacity;      /* bytes of per-warp staging (ring of source rows in flight); 0 = default (3584) */
+  int32_t rowbuf_capacity;      /* bytes of per-warp staging (ring of source rows in flight); 0 = default (2800) */
 
   /* sources: a table of descriptors (ragged batch) or, if NULL, one descriptor + stride (stacked [B,H,W] tensor) */
   const B200AugSrc* src_table;
@@ -135,7 +140,7 @@ typedef struct B200AugFusedArgs {
   int32_t n_fields;
   int32_t roi_field;            /* index into fields of the focus box (roi_variable), -1 if F_ROI_FROM_LANDMARKS only */
   int32_t landmark_field;       /* index of pt3d_68 for F_ROI_FROM_LANDMARKS, else -1 */
-  int32_t cluster_size;         /* CTAs (thread-block cluster) that share one sample: 1, 2 or 4; 0 = default (2) */
+  int32_t cluster_size;         /* CTAs (thread-block cluster) that share one sample: 1, 2, 4 or 8; 0 = default (2) */
   B200AugField fields[B200AUG_MAX_FIELDS];
 
   /* outputs (each may be NULL) */
@@ -146,23 +151,33 @@ typedef struct B200AugFusedArgs {
   float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
   int32_t* status_out;          /* [B] B200AUG_S_* */
   uint64_t* trace_out;          /* [B*cluster_size,16] per-CTA timeline for profiling: %globaltimer (ns) at start / plan built / cluster
-                                   synchronised / resample done / end, then %smid, warp stage done, tables+columns built, resize tables
-                                   built, labels done, photometric LUT built; the rest 0 */
+                                   synchronised / resample done / end, then %smid, (unused), canvas ready, resize tables
+                                   built, (unused), photometric LUT built; the rest 0 */
   /* optional launch order: order[i] = sample processed by the i-th cluster of the grid (a permutation of 0..B-1).  The
    * CTAs are dispatched in grid order, so listing the expensive samples (rotated, blurred, noisy) first lets the cheap
    * ones fill the tail.  NULL = identity. */
   const int32_t* order;
   /* optional scratch for rotated samples: B regions of workspace_stride bytes (see b200aug_workspace_stride()).  The
    * two-stage rotated path (warpAffine canvas, then INTER_AREA; image_geometric_cv2.py:121-134) keeps its canvas here,
-   * i.e. in L2.  Without it (NULL) or when a canvas does not fit, canvas rows are produced one at a time instead. */
+   * i.e. in L2: a kernel of its own (warp_kernel, needs `plans` too) fills the canvases while the fused kernel already
+   * resamples the unrotated samples.  Without it (NULL) or when a canvas does not fit, canvas pixels are produced one at a
+   * time instead. */
   uint8_t* workspace;
   int64_t workspace_stride;
-  /* optional scratch for the plans: B records of plan_stride bytes (>= b200aug_plan_stride(out_w, out_h), a multiple of
-   * 16).  When given (and an image is produced) a small kernel computes every sample's plan and cv2 resize tables first
-   * and the fused kernel loads them, instead of every CTA building them behind its full register / shared-memory
-   * footprint.  NULL = build them inside the fused kernel. */
+  /* optional scratch for the plans: b200aug_plan_buffer_bytes(batch, out_w, out_h) bytes = B records of plan_stride bytes
+   * (= b200aug_plan_stride(out_w, out_h), a multiple of 16) followed by a small tail (work counters and per-sample flags
+   * of warp_kernel).  A small kernel computes every sample's plan, cv2 resize tables and LABELS first (it always runs: the
+   * labels are its output); with this buffer it also leaves the records for the fused kernel to load, instead of every CTA
+   * rebuilding them behind its full register / shared-memory footprint.  NULL = build them inside the fused kernel. */
   uint8_t* plans;
   int64_t plan_stride;
+  int32_t warp_ctas;            /* CTAs of the fused grid that produce the rotated samples' canvases instead of taking a sample
+                                   (canvas workers); 0 = default (1.5 per SM), < 0 = none */
+  int32_t phase;                /* B200AUG_PHASE_*: 0 = the whole call; PLAN = plan_kernel only (plans + tables + labels + side
+                                   outputs), MAIN = everything behind it (needs the records a PLAN call with the same arguments
+                                   left in `plans`).  A caller that pipelines steps runs PLAN of step s + 1 on a second stream
+                                   next to MAIN of step s: plan_kernel is a short latency-bound grid that fits into the tail of
+                                   the big kernel. */
 
   B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
 } B200AugFusedArgs;
@@ -175,8 +190,9 @@ int b200aug_last_cuda_error(void);
 size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capacity);
 /* bytes of scratch per sample that hold the rotated canvas of a crop box of up to max_side x max_side source pixels */
 int64_t b200aug_workspace_stride(int max_side);
-/* bytes of one record of B200AugFusedArgs::plans for this output size */
+/* bytes of one record of B200AugFusedArgs::plans for this output size, and of the whole buffer for `batch` samples */
 int64_t b200aug_plan_stride(int out_w, int out_h);
+int64_t b200aug_plan_buffer_bytes(int batch, int out_w, int out_h);
 
 /* Host -> device upload of the rows the fused kernel will read, instead of whole frames (Batch.to(device),
  * datasets/batch.py:161-165 / pipelines.py:508): for each of `batch` stacked frames (host_frames: PINNED host memory,
@@ -186,7 +202,11 @@ int64_t b200aug_plan_stride(int out_w, int out_h);
 int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
                              int32_t batch, const int32_t* row_lo, const int32_t* row_hi, void* stream);
 
-/* The fused hot path: one launch, one CTA per sample.
+/* The fused hot path.  Up to three kernels, chained with programmatic dependent launches on `stream`:
+ *   plan_kernel   one small CTA per sample: view box, transforms, cv2 resize tables, all label transforms, side outputs
+ *   warp_kernel   (rotated samples, needs plans + workspace) cv2.warpAffine canvases, persistent work-stealing grid
+ *   fused_augment_kernel   one cluster per sample: cv2.resize -> flip/rot90 -> normalise -> photometric chain -> whiten
+ * A call without an image output (labels only) runs plan_kernel alone.
  * Replaces, per the flags: batch/normalization.py:83-90, batch/misc.py:9-31, batch/geometric.py:107-231
  * (+ tensors/image_geometric_cv2.py:28-155 incl. cv2.warpAffine / cv2.resize arithmetic, tensors/affinetrafo.py:37-148),
  * batch/geometric.py:234-267, batch/normalization.py:20-56, batch/intensity.py:30-64, batch/normalization.py:94-99. */

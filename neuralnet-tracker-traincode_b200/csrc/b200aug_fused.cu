@@ -44,7 +44,6 @@ constexpr int DEFAULT_ROWBUF = 2800;  // per-warp staging bytes: a ring of RING_
 constexpr int RING_D = 4;          // canvas rows in flight per warp (cp.async commit groups)
 constexpr int ROWPROG_CAP = 96;    // canvas rows one warp can stream per band (its vertical-pass program, 8 B per row)
 constexpr int DEFAULT_CLUSTER = 2;  // CTAs sharing one sample
-constexpr int LAB_CAP = 1024;      // floats of label data staged in shared memory while the plan is being built
 
 // bytes of one ring slot for a row segment of `seg_bytes`: alignment shift (<= 15) + 16-byte granular copy + tap over-read
 __host__ __device__ __forceinline__ int ring_slot_bytes(int seg_bytes) { return (seg_bytes + 15 + 15 + ROWBUF_SLACK) & ~15; }
@@ -80,10 +79,17 @@ struct Plan {
   float gamma, contrast, brightness_shift;
   int noise_on[B200AUG_NUM_NOISE];
   int any_noise;
+  // rotated samples: where the canvas workers leave the cv2.warpAffine canvas (this sample's region of the workspace);
+  // NULL = no scratch canvas (no workspace, or it does not fit): the per-pixel path produces canvas pixels on the fly
+  uint8_t* cv_ptr;
+  int cv_pitch;
+  int cv_pad;
 };
 
+constexpr size_t WORKER_AREA = 2 * 512 * 8 + 1024 * 2 + 512 + 3 * 9392;  // = WK_AREA_BYTES (checked where that is defined)
+
 struct SmemLayout {
-  size_t off_tabs, off_tile, off_rowbuf, off_dtab, off_bars, off_lab, off_prog, total;
+  size_t off_tabs, off_tile, off_rowbuf, off_bars, off_prog, total;
   int ntab;
 };
 
@@ -100,12 +106,9 @@ __host__ __device__ inline SmemLayout smem_layout(int ow, int oh, int cap) {
   o += ((size_t)ow * oh + 15) & ~size_t(15);
   L.off_rowbuf = o;
   o += (size_t)NWARPS * (cap + ROWBUF_SLACK);
-  L.off_dtab = o;
-  o += (size_t)DT_CAP * sizeof(int2);
+  if (o < L.off_tile + WORKER_AREA) o = L.off_tile + WORKER_AREA;  // a canvas worker's tables + staged tiles alias tile + row buffers
   L.off_bars = o;
   o += 2 * sizeof(uint64_t);  // the cluster exchange barrier
-  L.off_lab = o;
-  o += (size_t)LAB_CAP * sizeof(float);
   L.off_prog = o;
   o += (size_t)NWARPS * ROWPROG_CAP * sizeof(float2);
   L.total = o;
@@ -160,8 +163,12 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
   }
 }
 
+// per-CTA timeline (profiling aid): compiled into the TRACE instantiation of the kernel only
+template <bool TRACE>
 __device__ __forceinline__ void trace_mark(const B200AugFusedArgs& a, int slot) {
-  if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)blockIdx.x * 16 + slot] = globaltimer_ns();
+  if (TRACE) {
+    if (a.trace_out && threadIdx.x == 0) a.trace_out[(size_t)blockIdx.x * 16 + slot] = globaltimer_ns();
+  }
 }
 
 // ---- thread-block clusters: the CTAs of a cluster share one sample (each resamples a band of rows and stores the
@@ -444,10 +451,11 @@ __device__ void run_item_chain(const Plan& P, uint32_t flags, int category, floa
   if (flags & B200AUG_F_NORMALIZE) transform_item(P.t3, category, v, dim);
 }
 
-// `staged`: the transformable fields of this sample, packed in field order in shared memory (or NULL).
-// All items of all transformable fields form one flat list that the threads of the CTA share (one pass for the pose
-// pipeline's 68 + 1 + 1 + 1 items): the fields are not walked one after the other.
-__device__ __noinline__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b, const float* staged) {
+// All items of all transformable fields of one sample form one flat list that the threads [t0, t0 + nt) of the CTA share (one
+// pass for the pose pipeline's 68 + 1 + 1 + 1 items): the fields are not walked one after the other.  Runs in plan_kernel.
+__device__ __noinline__ void transform_labels(const B200AugFusedArgs& a, const Plan& P, int b, int t0, int nt) {
+  const int tl = (int)threadIdx.x - t0;
+  if (tl < 0 || tl >= nt) return;
   // an odd number of mirroring transforms permutes the left/right landmarks
   const bool flip_parity = (((a.flags & B200AUG_F_FOCUS) && P.t1.det < 0.f) + (P.has_t2 && P.t2.det < 0.f)) & 1;
   int total = 0;
@@ -458,26 +466,25 @@ __device__ __noinline__ void transform_labels(const B200AugFusedArgs& a, const P
       const float* in = F.in + (size_t)b * F.count * F.dim;
       float* out = F.out + (size_t)b * F.count * F.dim;
       if (in != out)
-        for (int i = threadIdx.x; i < F.count * F.dim; i += NTHREADS) out[i] = in[i];
+        for (int i = tl; i < F.count * F.dim; i += nt) out[i] = in[i];
       continue;
     }
     total += F.count;
   }
-  for (int t = threadIdx.x; t < total; t += NTHREADS) {
-    // locate item t: field f, index i, offset of the field in the staged copy
-    int f = 0, i = t, off = 0;
+  for (int t = tl; t < total; t += nt) {
+    // locate item t: field f, index i
+    int f = 0, i = t;
     for (; f < a.n_fields; ++f) {
       const B200AugField& F = a.fields[f];
       if (!F.out || !F.in || F.category == B200AUG_CAT_GENERAL || F.dim > 4) continue;
       if (i < F.count) break;
       i -= F.count;
-      off += F.count * F.dim;
     }
     const B200AugField& F = a.fields[f];
     const bool is_roi_from_lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && f == a.roi_field;
-    if (is_roi_from_lm) continue;  // written by warp 2 in the prologue
+    if (is_roi_from_lm) continue;  // written by warp 2 of build_plan
     const int dim = F.dim, cnt = F.count, cat = F.category;
-    const float* in = staged ? staged + off : F.in + (size_t)b * cnt * dim;
+    const float* in = F.in + (size_t)b * cnt * dim;
     float* out = F.out + (size_t)b * cnt * dim;
     const int si = (cat == B200AUG_CAT_POINTS && cnt == 68 && flip_parity) ? flip_map68(i) : i;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -849,10 +856,11 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 // DIRECT: the sample's photometric chain is one point function (no equalize / blur / noise) and there is no 90-degree
 // rotation, so the finished uint8 pixel goes through the (already built) LUT straight to the float32 output `gimg` --
 // no tile, no cluster exchange, no separate output pass.
-template <int K, bool DIRECT>
+template <int K>
 __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int ow_band, int warp, int lane, int cr, int cl,
                                        float* __restrict__ gimg) {
-  const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4)
+  const bool DIRECT = gimg != nullptr;  // (a run-time flag: one instantiation per K keeps the hot code small)
+  const int cs = 31 - __clz(cl);  // log2 of the cluster size
   const int rows_lo = (cr * oh) >> cs, rows_n = (((cr + 1) * oh) >> cs) - rows_lo;  // this CTA's band of output rows
   const int dy_begin = rows_lo + (warp * rows_n) / NWARPS, dy_end = rows_lo + ((warp + 1) * rows_n) / NWARPS;
   if (dy_begin >= dy_end) return;
@@ -913,7 +921,6 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     const int seg_lo = max(T.start[g0], cfl);
     const int seg_hi = max(min(T.start[glast] + (T.n[glast] & 0xffff), cfh), seg_lo);
     const int seg_bytes = seg_hi - seg_lo;
-    int xb[RMAX];        // first tap of the column, relative to the segment
     // the lane's columns are g0 + lane + 32 j, j < nvalid; their pixels in the tile row being accumulated sit at
     // trow32 + j * cstep (shared-memory address, flip / rot90 folded in)
     const int nvalid = (gcols - lane + 31) >> 5;
@@ -922,23 +929,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     // DIRECT: the same pixel as a float32 in global memory, and the LUT behind the plan in shared memory
     float* grow = DIRECT ? gimg + (tm.o + (g0 + lane) * tm.sb + dy_begin * tm.sa) : nullptr;
     const uint32_t lut32 = smem_u32(smem + ((sizeof(Plan) + 15) & ~size_t(15)));
-    float w[RMAX][K];
-#pragma unroll
-    for (int j = 0; j < RMAX; ++j) {
-      const int dx = g0 + 32 * j + lane;
-      const bool valid = dx <= glast;
-      const int dxc = valid ? dx : g0;
-      const int xnf = T.n[dxc], xn = xnf & 0xffff;
-      const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
-      const float xaf = T.a[dxc], xam = T.b[dxc], xal = T.c[dxc];
-      const int xs = T.start[dxc];
-      xb[j] = xs - seg_lo;
-#pragma unroll
-      for (int t = 0; t < K; ++t) {
-        const int col = xs + t;
-        w[j][t] = (valid && t < xn && col >= cfl && col < cfh) ? area_alpha(t, xn, xhf, xhl, xaf, xam, xal) : 0.f;
-      }
-    }
+    int xb[RMAX];        // first tap of the column, relative to the segment
     // ring geometry: every fetched row is copied as `nvec` 16-byte vectors starting at the 16-byte boundary at or below
     // its first byte, so the copy ends less than 16 * nvec bytes after the segment's first byte
     // (the caller checked that RING_D slots fit the warp's row buffer and that nvec <= 64)
@@ -1025,6 +1016,24 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     };
     __syncwarp();
     for (int i = 0; i < D; ++i) issue(i * slot_bytes, ga + (ptrdiff_t)i * pitch, R0 + i >= f_lo && R0 + i <= f_hi);
+    // (the first rows are on their way: the tap weights are worked out while they fly)
+    float w[RMAX][K];
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      const int dx = g0 + 32 * j + lane;
+      const bool valid = dx <= glast;
+      const int dxc = valid ? dx : g0;
+      const int xnf = T.n[dxc], xn = xnf & 0xffff;
+      const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
+      const float xaf = T.a[dxc], xam = T.b[dxc], xal = T.c[dxc];
+      const int xs = T.start[dxc];
+      xb[j] = xs - seg_lo;
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const int col = xs + t;
+        w[j][t] = (valid && t < xn && col >= cfl && col < cfh) ? area_alpha(t, xn, xhf, xhl, xaf, xam, xal) : 0.f;
+      }
+    }
 
     int r = R0;
 #pragma unroll 1
@@ -1132,7 +1141,7 @@ __device__ __noinline__ float blurred_value(const uint8_t* tile, const float* lu
 // The plan of one sample, one branch per warp (see plan_core); also writes the per-sample side outputs (view box, focus
 // transform, back-transform, the roi regenerated from landmarks).  Runs either in plan_kernel (ahead of the fused kernel, so
 // that its latency chains do not occupy a big CTA slot) or at the top of the fused kernel itself.
-__device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, int warp, int lane, int cr, PlanCore* shared_core) {
+__device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Plan& P, int warp, int lane, bool side_out, PlanCore* shared_core) {
     float box[4] = {0.f, 0.f, 0.f, 0.f};
     const bool lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) && a.landmark_field >= 0;
     const bool half = a.flags & B200AUG_F_HALF_PIXEL;
@@ -1163,26 +1172,29 @@ __device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Pla
         const AffDerived d1 = aff_derive(c.t1);
         if (lane == 0) {
           P.t1 = d1;
-          if (a.view_roi_out && focus) {
+          P.cv_ptr = nullptr;
+          P.cv_pitch = 0;
+          P.cv_pad = 0;
+          if (side_out && a.view_roi_out && focus) {
             int32_t* o = a.view_roi_out + 4 * (size_t)b;
             o[0] = c.vx0; o[1] = c.vy0; o[2] = c.vx1; o[3] = c.vy1;
           }
-          if (a.tr_out && focus) {
+          if (side_out && a.tr_out && focus) {
             float* o = a.tr_out + 6 * (size_t)b;
             o[0] = c.t1.a00; o[1] = c.t1.a01; o[2] = c.t1.a02; o[3] = c.t1.a10; o[4] = c.t1.a11; o[5] = c.t1.a12;
           }
-          if (a.backtransform_out && focus) {
+          if (side_out && a.backtransform_out && focus) {
             Aff iv = aff_inv(c.t1);
             float* o = a.backtransform_out + 6 * (size_t)b;
             o[0] = iv.a00; o[1] = iv.a01; o[2] = iv.a02; o[3] = iv.a10; o[4] = iv.a11; o[5] = iv.a12;
           }
         }
-        if (lm && a.roi_field >= 0 && a.fields[a.roi_field].out) {
+        if (side_out && lm && a.roi_field >= 0 && a.fields[a.roi_field].out) {
           // landmarks mode: the roi label is regenerated from the transformed landmarks after the crop (pipelines.py:347-351)
           const B200AugField& F = a.fields[a.landmark_field];
           float nb[4];
           landmark_box(F.in + (size_t)b * F.count * F.dim, F.count, F.dim, half, focus ? &d1 : nullptr, nb);
-          if (lane == 0 && cr == 0) {
+          if (lane == 0) {
             if ((a.flags & B200AUG_F_FLIPROT) && (c.do_flip || c.rot_dir != 0)) tf_roi(aff_derive(fliprot_transform(c)), nb);
             if (a.flags & B200AUG_F_NORMALIZE) tf_roi(aff_derive(normalize_transform(c)), nb);
             float* o = a.fields[a.roi_field].out + 4 * (size_t)b;
@@ -1207,7 +1219,7 @@ __device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Pla
   }
 
 // cv2's per-axis resize tables of one sample (x entries first, then y), and Plan::kx
-__device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P, const Tabs& T, int tid, int lane) {
+__device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P, const Tabs& T, int tid, int lane, int nthr) {
   const int ow = a.out_w, oh = a.out_h;
   const int rs = P.rs_mode;
   if (rs == RS_AREA || rs == RS_LINEAR || rs == RS_AREA_INT) {
@@ -1236,8 +1248,8 @@ __device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P,
     };
     const int ntab = ow + oh;
     if (rs == RS_AREA) {
-      for (int i = tid; i < ntab; i += 2 * NTHREADS) {
-        const int i2 = i + NTHREADS;
+      for (int i = tid; i < ntab; i += 2 * nthr) {
+        const int i2 = i + nthr;
         const bool two = i2 < ntab;
         const int j = two ? i2 : i;  // (a lone entry is simply computed twice)
         const bool x1 = i < ow, x2 = j < ow;
@@ -1252,7 +1264,7 @@ __device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P,
         if (lane == 0 && kmax) atomicMax(&P.kx, kmax);
       }
     } else {
-      for (int i = tid; i < ntab; i += NTHREADS) tab_entry(i);
+      for (int i = tid; i < ntab; i += nthr) tab_entry(i);
     }
   }
 }
@@ -1261,12 +1273,39 @@ __device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P,
 __host__ __device__ inline size_t plan_bytes() { return (sizeof(Plan) + 15) & ~size_t(15); }
 __host__ __device__ inline size_t plan_tab_bytes(int ow, int oh) { return ((size_t)(ow + oh) * 5 * 4 + 15) & ~size_t(15); }
 
-// Plans + tables of all samples, one CTA per sample, ahead of the fused kernel (B200AugFusedArgs::plans).
-__global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ KArgs K) {
+// canvas geometry of a rotated sample in its workspace region: 16-byte aligned rows with room for the row copies' over-read
+__host__ __device__ __forceinline__ int canvas_pitch(int cw) { return (cw + 16 + 15) & ~15; }
+
+// The tail of B200AugFusedArgs::plans behind the B records: work-stealing counters of the canvas workers (one per slice
+// of WK_SLICE samples), one completion counter per sample, one "rotated, canvas in the workspace" flag byte per sample.
+constexpr int WK_SLICE = 1024;
+constexpr int WK_MAX_SLICES = 64;
+__host__ __device__ inline size_t plan_tail_bytes(int batch) {
+  return (size_t)WK_MAX_SLICES * 4 + (size_t)batch * 4 + (((size_t)batch + 15) & ~size_t(15));
+}
+struct PlanTail {
+  uint32_t* counters;  // [WK_MAX_SLICES] next work item of the slice
+  uint32_t* done;      // [B] chunks of the sample's canvas finished (WK_CHUNKS = complete)
+  uint8_t* flags;      // [B] 1 = rotated sample with a canvas in the workspace
+};
+__host__ __device__ inline PlanTail plan_tail(unsigned char* plans, int batch, int64_t plan_stride) {
+  unsigned char* t = plans + (size_t)batch * plan_stride;
+  PlanTail r;
+  r.counters = reinterpret_cast<uint32_t*>(t);
+  r.done = r.counters + WK_MAX_SLICES;
+  r.flags = reinterpret_cast<uint8_t*>(r.done + batch);
+  return r;
+}
+
+// Plans + resize tables + LABELS of all samples, one CTA per sample, ahead of the other kernels.  The labels only need the
+// plan's transforms, so they are finished here (the big kernels never touch them); the record (plan + tables) goes to
+// B200AugFusedArgs::plans when that buffer is given.
+__global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ KArgs K, int with_tables) {
   const B200AugFusedArgs& a = K.a;
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ntab = a.out_w + a.out_h;
+  const int ntab = with_tables ? a.out_w + a.out_h : 0;
+  const size_t tab_bytes = with_tables ? plan_tab_bytes(a.out_w, a.out_h) : 0;
   Plan& P = *reinterpret_cast<Plan*>(smem);
   Tabs T;
   T.start = reinterpret_cast<int*>(smem + plan_bytes());
@@ -1274,36 +1313,376 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
   T.a = reinterpret_cast<float*>(T.n + ntab);
   T.b = T.a + ntab;
   T.c = T.b + ntab;
-  // programmatic dependent launch: the fused kernel may be scheduled now; it waits (griddepcontrol.wait) for this whole grid
+  // programmatic dependent launch: the next kernel may be scheduled now; it waits (griddepcontrol.wait) for this whole grid
   // to complete and flush before it reads the plans
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  build_plan(a, b, P, warp, lane, 0, reinterpret_cast<PlanCore*>(smem + plan_bytes() + plan_tab_bytes(a.out_w, a.out_h)));
+  PlanTail tail = {nullptr, nullptr, nullptr};
+  if (a.plans) tail = plan_tail(a.plans, a.batch, a.plan_stride);
+  if (a.plans && b == 0 && tid < WK_MAX_SLICES) tail.counters[tid] = 0u;  // the canvas workers' work counters
+  build_plan(a, b, P, warp, lane, true, reinterpret_cast<PlanCore*>(smem + plan_bytes() + tab_bytes));
   __syncthreads();
-  build_tables(a, P, T, tid, lane);
-  __syncthreads();
-  const int nvec = (int)((plan_bytes() + plan_tab_bytes(a.out_w, a.out_h)) >> 4);
-  uint4* dst = reinterpret_cast<uint4*>(a.plans + (size_t)b * a.plan_stride);
-  const uint4* src = reinterpret_cast<const uint4*>(smem);
-  for (int i = tid; i < nvec; i += NTHREADS) dst[i] = src[i];
+  if (tid == 0) {
+    // rotated samples: the canvas goes to this sample's workspace region (if it fits), the canvas workers fill it
+    bool canvas = false;
+    if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.status == B200AUG_S_OK && P.cw <= DT_CAP) {
+      const int spitch = canvas_pitch(P.cw);
+      if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
+        P.cv_ptr = a.workspace + (size_t)b * a.workspace_stride;
+        P.cv_pitch = spitch;
+        canvas = true;
+      }
+    }
+    if (a.plans) {
+      tail.flags[b] = canvas ? 1 : 0;
+      tail.done[b] = 0u;
+    }
+    if (a.status_out) a.status_out[b] = P.status;
+  }
+  // the labels (warps 5-7) next to the resize tables (warps 0-4): both only read the finished plan
+  transform_labels(a, P, b, 5 * 32, 3 * 32);
+  if (with_tables) {
+    if (tid < 5 * 32) build_tables(a, P, T, tid, lane, 5 * 32);
+    __syncthreads();
+    if (a.plans) {
+      const int nvec = (int)((plan_bytes() + tab_bytes) >> 4);
+      uint4* dst = reinterpret_cast<uint4*>(a.plans + (size_t)b * a.plan_stride);
+      const uint4* src = reinterpret_cast<const uint4*>(smem);
+      for (int i = tid; i < nvec; i += NTHREADS) dst[i] = src[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ canvas workers
+
+// cv2.warpAffine of every rotated sample's canvas into its workspace region.  Some CTAs of the fused kernel's grid take
+// this role instead of a sample (fused_augment_kernel decides which): work items = (rotated sample, quarter of its canvas
+// tiles) handed out by an atomic counter, so the stage is spread over the whole machine instead of sitting in front of its
+// own sample's resampling (where one rotated + blurred sample used to bound the whole launch).  The samples are found by
+// scanning the flag bytes plan_kernel left behind the plan records; every finished item bumps its sample's completion
+// counter, which the sample's own CTAs wait for (a worker is always among the first CTAs of the grid and any worker can
+// take any item, so the wait cannot deadlock).
+//
+// One item is a pipeline over 64 x 32 canvas tiles: the canvas has the resolution of the source (image_geometric_cv2.py:
+// 121-124 sizes it so), so a tile's source footprint is a rotated 64 x 32 rectangle; its bounding box (<= 74 rows x 81 px)
+// is staged in shared memory by all threads with 16-byte cp.async copies, WK_NSTAGE - 1 tiles ahead of the tile being
+// gathered, so the loads' latency never sits in front of the arithmetic.  Box rows outside the frame are zero-filled by the
+// copy itself (src-size 0 = BORDER_CONSTANT), columns outside it by a fix-up pass over the staged box, so the gather loop
+// is the same for every tile: per 32 pixels 2 adds, 3 address ops, 4 byte loads, the 11-op fixed-point blend, 1 store.
+// Staged layout (as warp_canvas_to_scratch): box row r lands at offset B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift
+// of row 0, pm = pitch mod 16, so that source pixel (iy, ix) sits at c0 + (iy - by0)(B + pm) + (ix - bx0): linear, no
+// per-row alignment fix-up in the gather; B is 96 or 112, whichever spreads one canvas row's taps over more banks.
+constexpr int WK_CHUNKS = 2;                 // work items per rotated sample
+constexpr int WK_NSTAGE = 3;                 // staged tiles in flight per worker
+constexpr int WT2_W = 64, WT2_H = 32;        // canvas tile of one pipeline step
+constexpr int WT2_ROWS = 74;                 // tallest staged bounding box
+constexpr int WT2_NCH = 6;                   // 16-byte chunks staged per box row (box width + alignment shift <= 96)
+constexpr int WT2_B0 = 96, WT2_B1 = 112;     // candidate row strides (+ pitch mod 16)
+constexpr int WT2_STAGE = ((WT2_ROWS - 1) * (WT2_B1 + 15) + 15 + 16 * WT2_NCH + 15) & ~15;
+constexpr int WK_OFF_RTAB = DT_CAP * 8, WK_OFF_LIST = 2 * DT_CAP * 8, WK_OFF_SH = WK_OFF_LIST + WK_SLICE * 2,
+              WK_OFF_STAGE = WK_OFF_SH + 512, WK_AREA_BYTES = WK_OFF_STAGE + WK_NSTAGE * WT2_STAGE;
+
+static_assert(WK_AREA_BYTES == (int)WORKER_AREA, "smem_layout reserves WORKER_AREA bytes for a canvas worker");
+
+struct TileMeta {
+  int x_lo, y_lo, tw, th, bx0, bx1, by0, c0, nrows, mode;  // mode 0 staged | 1 staged, columns outside the frame | 2 not staged
+  int pad[2];
+};
+
+// geometry of canvas tile (tx, ty): bounding box of its taps in the source, staging decision.  One thread.
+__device__ __forceinline__ void wk_tile_meta(const Plan& P, const int2* dtab, const int2* rtab, int tx, int ty, TileMeta* meta) {
+  const int x_lo = tx * WT2_W, y_lo = ty * WT2_H;
+  const int tw = min(WT2_W, P.cw - x_lo), th = min(WT2_H, P.ch - y_lo);
+  // bounding box of the taps from the four tile corners (the fixed-point map is monotone in x and in y)
+  const int2 ra = rtab[y_lo], rb = rtab[y_lo + th - 1], dl = dtab[x_lo], dr = dtab[x_lo + tw - 1];
+  const int ix0 = (ra.x + dl.x) >> 10, ix1 = (ra.x + dr.x) >> 10, ix2 = (rb.x + dl.x) >> 10, ix3 = (rb.x + dr.x) >> 10;
+  const int iy0 = (ra.y + dl.y) >> 10, iy1 = (ra.y + dr.y) >> 10, iy2 = (rb.y + dl.y) >> 10, iy3 = (rb.y + dr.y) >> 10;
+  const int bx0 = min(min(ix0, ix1), min(ix2, ix3)), bx1 = max(max(ix0, ix1), max(ix2, ix3)) + 1;
+  const int by0 = min(min(iy0, iy1), min(iy2, iy3)), by1 = max(max(iy0, iy1), max(iy2, iy3)) + 1;
+  const int nrows = by1 - by0 + 1, bbw = bx1 - bx0 + 1;
+  const uintptr_t gbase = reinterpret_cast<uintptr_t>(P.src) + (ptrdiff_t)by0 * P.pitch + bx0;  // (may lie outside the frame)
+  const bool staged = nrows <= WT2_ROWS && bbw + 15 <= 16 * WT2_NCH;
+  TileMeta m;
+  m.x_lo = x_lo; m.y_lo = y_lo; m.tw = tw; m.th = th; m.bx0 = bx0; m.bx1 = bx1; m.by0 = by0; m.c0 = (int)(gbase & 15); m.nrows = nrows;
+  m.mode = !staged ? 2 : ((bx0 < 0 || bx1 >= P.sw) ? 1 : 0);
+  m.pad[0] = m.pad[1] = 0;
+  *meta = m;
+}
+
+// the cp.async copies of a tile's source box into its stage: thread = (16-byte chunk k = tid & 7, rows tid >> 3 + 32 j)
+__device__ __forceinline__ void wk_issue_tile(const Plan& P, const TileMeta& m, int bstride, uint32_t buf32, int tid) {
+  if (m.mode == 2) return;
+  const int k = tid & 7;
+  if (k >= WT2_NCH) return;
+  const int pitch = P.pitch, sh = P.sh, pm = pitch & 15, by0 = m.by0, c0 = m.c0, nrows = m.nrows;
+  const uintptr_t src = reinterpret_cast<uintptr_t>(P.src);
+  // copies must stay inside the 16-byte blocks that hold frame bytes; everything else is zero-filled
+  const uintptr_t frame_lo = src & ~uintptr_t(15), frame_end = src + (size_t)(sh - 1) * pitch + P.sw;
+  int row = tid >> 3;
+  uintptr_t grow = src + (ptrdiff_t)(by0 + row) * pitch + m.bx0;      // first byte of box row `row`
+  uint32_t drow = buf32 + (uint32_t)(row * bstride + 16 * k), sft = (uint32_t)(c0 + row * pm);
+  const uint32_t drow_step = 32u * (uint32_t)bstride, sft_step = 32u * (uint32_t)pm;
+  const ptrdiff_t grow_step = (ptrdiff_t)32 * pitch;
+#pragma unroll 1
+  for (; row < nrows; row += 32) {
+    const uintptr_t g = (grow & ~uintptr_t(15)) + 16u * (uint32_t)k;
+    const bool ok = (unsigned)(by0 + row) < (unsigned)sh && g >= frame_lo && g < frame_end;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + ((sft >> 4) << 4)), "l"(ok ? g : frame_lo), "r"(ok ? 16 : 0)
+                 : "memory");
+    grow += grow_step;
+    drow += drow_step;
+    sft += sft_step;
+  }
+}
+
+__device__ __forceinline__ void wk_compute_tile(const Plan& P, const int2* dtab, const int2* rtab, const TileMeta* meta, int bstride,
+                                                uint8_t* buf, int warp, int lane, int tid) {
+  uint8_t* const canvas = P.cv_ptr;
+  const int spitch = P.cv_pitch;
+  const TileMeta m = *meta;  // (registers: the gather loop's inline assembly would otherwise force reloads)
+  if (m.mode == 2) {
+    // (a box too large to stage: only for strongly down-scaling canvases, which image_geometric_cv2.py never builds)
+    const uint8_t* const src = P.src;
+    const int pitch = P.pitch, sw = P.sw, sh = P.sh;
+    for (int p = tid; p < m.tw * m.th; p += NTHREADS) {
+      const int yy = p / m.tw, xx = p - yy * m.tw;
+      const int2 ro = rtab[m.y_lo + yy], d = dtab[m.x_lo + xx];
+      const int X = (ro.x + d.x) >> 5, Y = (ro.y + d.y) >> 5, ix = X >> 5, iy = Y >> 5;
+      const bool r0 = (unsigned)iy < (unsigned)sh, r1 = (unsigned)(iy + 1) < (unsigned)sh;
+      const bool q0 = (unsigned)ix < (unsigned)sw, q1 = (unsigned)(ix + 1) < (unsigned)sw;
+      const uint8_t* g = src + (ptrdiff_t)iy * pitch + ix;
+      const int p00 = (r0 && q0) ? __ldg(g) : 0, p01 = (r0 && q1) ? __ldg(g + 1) : 0;
+      const int p10 = (r1 && q0) ? __ldg(g + pitch) : 0, p11 = (r1 && q1) ? __ldg(g + pitch + 1) : 0;
+      canvas[(size_t)(m.y_lo + yy) * spitch + m.x_lo + xx] = (uint8_t)bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
+    }
+    return;
+  }
+  const int rstride = bstride + (P.pitch & 15);
+  if (m.mode == 1) {
+    // BORDER_CONSTANT: the staged bytes of columns outside [0, sw) belong to neighbouring rows -- zero them
+    const int nl = max(0, min(m.bx1, -1) - m.bx0 + 1);
+    const int xr = max(P.sw, m.bx0), nr = max(0, m.bx1 - xr + 1), nz = nl + nr;
+    for (int i = tid; i < m.nrows * nz; i += NTHREADS) {
+      const int r = i / nz, j = i - r * nz;
+      const int x = (j < nl) ? m.bx0 + j : xr + (j - nl);
+      buf[m.c0 + r * rstride + (x - m.bx0)] = 0;
+    }
+    __syncthreads();
+  }
+  // shared-memory address of source pixel (iy, ix) = buf + c0 + (iy - by0) * rstride + (ix - bx0).  The low 22 bits of the
+  // base, c0 - bx0 and -by0 ride in the column deltas (scaled by 1024 like the coordinates); the high bits of the base (in
+  // a cluster the shared-memory window of a CTA carries its rank up there) come back in through the funnel shift that
+  // extracts the integer coordinate, so the address costs shift + shift + multiply-add.
+  const uint32_t buf32 = smem_u32(buf), hi22 = buf32 >> 22;
+  const uint32_t K = (buf32 & 0x3FFFFFu) + (uint32_t)(m.c0 - m.bx0);
+  int dxk[2], dyk[2];
+  bool act[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int xi = 32 * h + lane;
+    const int2 d = dtab[m.x_lo + min(xi, m.tw - 1)];  // (idle lanes repeat the last column: their addresses stay valid)
+    dxk[h] = d.x + (int)(K << 10);
+    dyk[h] = d.y - (m.by0 << 10);
+    act[h] = xi < m.tw;
+  }
+  const uint32_t ro32 = smem_u32(rtab + m.y_lo + warp);
+  uint8_t* out = canvas + (size_t)(m.y_lo + warp) * spitch + m.x_lo + lane;
+  const size_t out_step = (size_t)NWARPS * spitch;
+  const int n_it = (m.th - warp + NWARPS - 1) / NWARPS;  // rows warp, warp + 8, ...
+#pragma unroll 2
+  for (int it = 0; it < n_it; ++it) {
+    int rox, roy;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(rox), "=r"(roy) : "r"(ro32 + (uint32_t)it * (NWARPS * 8)) : "memory");
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t sx = (uint32_t)rox + (uint32_t)dxk[h];  // 1/1024 px, offset by K
+      const int sy = roy + dyk[h];
+      const uint32_t a0 = (uint32_t)(sy >> 10) * (uint32_t)rstride + __funnelshift_r(sx, hi22, 10), a1 = a0 + (uint32_t)rstride;
+      uint32_t p00, p01, p10, p11;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a0) : "memory");
+      asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(a0) : "memory");
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a1) : "memory");
+      asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p11) : "r"(a1) : "memory");
+      // bilinear_q5 with the 1/32 fractions left in place (fx32 = 32 fx): every term carries a factor 1024
+      const int fx = sx & 0x3E0, fy = sy & 0x3E0;
+      const int top = (1024 - fx) * (int)p00 + fx * (int)p01, bot = (1024 - fx) * (int)p10 + fx * (int)p11;
+      const int q = ((1024 - fy) * top + fy * bot + (512 << 10)) >> 20;
+      if (act[h]) out[32 * h] = (uint8_t)q;
+    }
+    out += out_step;
+  }
+}
+
+__device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, unsigned char* area, uint64_t* tr) {
+  int2* const dtab = reinterpret_cast<int2*>(area);
+  int2* const rtab = reinterpret_cast<int2*>(area + WK_OFF_RTAB);
+  uint16_t* const list = reinterpret_cast<uint16_t*>(area + WK_OFF_LIST);
+  int* const sh = reinterpret_cast<int*>(area + WK_OFF_SH);  // [0] n_list, [1] item, [2..9] warp counts, [10..17] bases
+  TileMeta* const meta = reinterpret_cast<TileMeta*>(area + WK_OFF_SH + 128);
+  uint8_t* const stage = area + WK_OFF_STAGE;
+  const uint32_t stage32 = smem_u32(stage);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const PlanTail tail = plan_tail(a.plans, a.batch, a.plan_stride);
+  int n_done = 0;
+  for (int slice = 0, base = 0; base < a.batch && slice < WK_MAX_SLICES; ++slice, base += WK_SLICE) {
+    // ---- the rotated samples of this slice of the launch order, in that order (every worker builds the same list)
+    if (tid == 0) sh[0] = 0;
+    __syncthreads();
+    const int n_here = min(WK_SLICE, a.batch - base);
+    for (int i0 = 0; i0 < n_here; i0 += NTHREADS) {
+      const int i = i0 + tid;
+      const bool on = i < n_here && tail.flags[a.order ? a.order[base + i] : base + i] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) sh[2 + warp] = __popc(m);
+      __syncthreads();
+      if (tid == 0) {
+        int run = sh[0];
+        for (int w = 0; w < NWARPS; ++w) { sh[10 + w] = run; run += sh[2 + w]; }
+        sh[0] = run;
+      }
+      __syncthreads();
+      if (on) list[sh[10 + warp] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+    }
+    __syncthreads();
+    const int n_items = sh[0] * WK_CHUNKS;
+    // ---- work stealing over (sample, chunk)
+    for (;;) {
+      if (tid == 0) sh[1] = (int)atomicAdd(&tail.counters[slice], 1u);
+      __syncthreads();
+      const int item = sh[1];
+      if (item >= n_items) break;
+      const int pos = base + list[item / WK_CHUNKS], chunk = item % WK_CHUNKS;
+      const int b = a.order ? a.order[pos] : pos;
+      {
+        const uint4* rec = reinterpret_cast<const uint4*>(a.plans + (size_t)b * a.plan_stride);
+        uint4* dst = reinterpret_cast<uint4*>(&P);
+        for (int i = tid; i < (int)(plan_bytes() >> 4); i += NTHREADS) dst[i] = rec[i];
+      }
+      __syncthreads();
+      // per-column / per-row fixed-point terms of cv2.warpAffine (oracle/cv2_model.py:warp_affine_linear_u8)
+      const int cw = P.cw, ch = P.ch;
+      for (int i = tid; i < cw + ch; i += NTHREADS) {
+        if (i < cw) {
+          dtab[i] = make_int2(rint_d2i(__dmul_rn(__dmul_rn(P.mi[0], (double)i), 1024.0)),
+                              rint_d2i(__dmul_rn(__dmul_rn(P.mi[3], (double)i), 1024.0)));
+        } else {
+          const double y = (double)(i - cw);
+          rtab[i - cw] = make_int2(rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[1], y), P.mi[2]), 1024.0)) + 16,
+                                   rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(P.mi[4], y), P.mi[5]), 1024.0)) + 16);
+        }
+      }
+      // Row stride of the staged box: whichever candidate spreads one canvas row's 32 taps over more shared-memory banks.
+      // The taps walk a straight line (mi[0] px right, mi[3] px down per canvas pixel), so the bank pattern depends on
+      // slope and stride only (every warp evaluates it; the result is the same).
+      int bstride = WT2_B0;
+      {
+        const int pm = P.pitch & 15;
+        const int ix = (int)floor(P.mi[0] * (double)lane), iy = (int)floor(P.mi[3] * (double)lane) + 64;
+        int best = INT_MAX;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int e = (c ? WT2_B1 : WT2_B0) + pm;
+          const unsigned word = (unsigned)(iy * e + ix) >> 2, bank = word & 31u;
+          const unsigned same_word = __match_any_sync(0xffffffffu, word), same_bank = __match_any_sync(0xffffffffu, bank);
+          const unsigned leaders = __ballot_sync(0xffffffffu, (__ffs(same_word) - 1) == lane);  // one lane per distinct word
+          const int degree = __reduce_max_sync(0xffffffffu, __popc(same_bank & leaders));      // wavefronts of this load
+          if (degree < best) { best = degree; bstride = c ? WT2_B1 : WT2_B0; }
+        }
+      }
+      __syncthreads();
+      const int tiles_x = (cw + WT2_W - 1) / WT2_W, tiles_y = (ch + WT2_H - 1) / WT2_H, n_tiles = tiles_x * tiles_y;
+      const int t_begin = (chunk * n_tiles) / WK_CHUNKS, t_end = ((chunk + 1) * n_tiles) / WK_CHUNKS;
+      // ---- the tile pipeline: the copies of tile t + WK_NSTAGE - 1 are issued before tile t is gathered; thread 0 works
+      // out the geometry of a tile (meta ring of WK_NSTAGE + 1) one step before its copies are issued
+      int mtx = 0, mty = 0, mt = t_begin;  // thread 0: the next tile to describe
+      if (tid == 0) {
+        mty = t_begin / tiles_x;
+        mtx = t_begin - mty * tiles_x;
+      }
+      auto describe = [&]() {
+        if (tid == 0 && mt < t_end) {
+          wk_tile_meta(P, dtab, rtab, mtx, mty, meta + (mt - t_begin) % (WK_NSTAGE + 1));
+          ++mt;
+          if (++mtx == tiles_x) { mtx = 0; ++mty; }
+        }
+      };
+      for (int s2 = 0; s2 < WK_NSTAGE; ++s2) describe();
+      __syncthreads();
+#pragma unroll 1
+      for (int s2 = 0; s2 < WK_NSTAGE - 1; ++s2) {
+        if (t_begin + s2 < t_end) wk_issue_tile(P, meta[s2], bstride, stage32 + s2 * WT2_STAGE, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+#pragma unroll 1
+      for (int t = t_begin; t < t_end; ++t) {
+        const int i = t - t_begin, sl = i % WK_NSTAGE, ia = i + WK_NSTAGE - 1, sn = ia % WK_NSTAGE;
+        const long long c0 = tr ? clock64() : 0;
+        if (t + WK_NSTAGE - 1 < t_end) wk_issue_tile(P, meta[ia % (WK_NSTAGE + 1)], bstride, stage32 + sn * WT2_STAGE, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        static_assert(WK_NSTAGE == 3, "wait_group immediate");
+        const long long c1 = tr ? clock64() : 0;
+        asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's copies of tile t have landed ...
+        __syncthreads();                                      // ... and everybody else's
+        const long long c2 = tr ? clock64() : 0;
+        wk_compute_tile(P, dtab, rtab, meta + i % (WK_NSTAGE + 1), bstride, stage + sl * WT2_STAGE, warp, lane, tid);
+        const long long c3 = tr ? clock64() : 0;
+        describe();       // tile t + WK_NSTAGE (its slot held tile t - 1, which nobody reads any more)
+        __syncthreads();  // the stage is free again, the new description visible
+        if (tr && tid == 0) {  // (profiling: cycles in issue / wait / gather / describe + barrier, tiles)
+          const long long c4 = clock64();
+          tr[8] += (uint64_t)(c1 - c0); tr[9] += (uint64_t)(c2 - c1); tr[10] += (uint64_t)(c3 - c2); tr[11] += (uint64_t)(c4 - c3); tr[12] += 1;
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();   // every thread's canvas pixels are written ...
+      if (tid == 0) {
+        __threadfence();  // ... and visible device-wide (cumulative over the barrier) before the completion counter moves
+        atomicAdd(&tail.done[b], 1u);
+      }
+      ++n_done;
+    }
+    __syncthreads();
+  }
+  if (tr && tid == 0) {
+    tr[4] = globaltimer_ns();
+    tr[2] = (uint64_t)n_done;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
 
-__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap, int lay_w, int lay_h) {
+// dep_mode: 1 = launched behind plan_kernel with a programmatic dependent launch: every CTA waits for it
+// (griddepcontrol.wait) before it reads its plan record; 0 = plain stream order (the plan is built in here)
+template <bool TRACE>
+__global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid_constant__ KArgs K, int cap, int dep_mode) {
   const B200AugFusedArgs& a = K.a;
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t cr_u, cl_u;
   cluster_info(cr_u, cl_u);
   const int cr = (int)cr_u, cl = (int)cl_u;  // rank in / size of the cluster that shares this sample
-  // launch order -> sample: the caller may schedule expensive samples (rotated, blurred) first so that the cheap ones
+  // launch order -> sample: the caller may schedule expensive samples (blurred, noisy) first so that the cheap ones
   // fill the tail of the grid
-  const int cs = cl >> 1;  // log2 of the cluster size (1, 2 or 4: checked at launch), divisions become shifts
-  const int b = a.order ? a.order[blockIdx.x >> cs] : (int)(blockIdx.x >> cs);
+  const int cs = 31 - __clz(cl);  // log2 of the cluster size (1, 2, 4 or 8: checked at launch), divisions become shifts
   const int ow = a.out_w, oh = a.out_h, npix = ow * oh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // (lay_w, lay_h) = (out_w, out_h) when an image is produced; label-only launches use a 1 x 1 layout so that label
-  // frames of any size (normalize_batch on 640 x 480 labels) never hit the shared-memory budget
-  const SmemLayout L = smem_layout(lay_w, lay_h, cap);
+  // a.warp_ctas CTAs of the grid (a multiple of the cluster size) produce the rotated samples' canvases instead of taking a
+  // sample.  They are interleaved with the sample clusters at the head of the grid -- worker, sample, sample, ... -- so
+  // that the first wave puts one worker next to two sample CTAs on every SM (three workers on one SM would all queue on
+  // its shared-memory pipe); cluster 0 is always a worker.
+  bool worker;
+  int slot;
+  {
+    const int nw = a.warp_ctas >> cs, ns = a.batch, g = min(nw, ns >> 1), c = (int)(blockIdx.x >> cs);
+    if (c < 3 * g) {
+      worker = (c % 3) == 0;
+      slot = c - (c / 3 + 1);
+    } else {
+      const int rem = c - 3 * g;
+      worker = rem < nw - g;
+      slot = 2 * g + rem - (nw - g);
+    }
+  }
+  const int b = worker ? 0 : (a.order ? a.order[slot] : slot);
+  const SmemLayout L = smem_layout(ow, oh, cap);
   Plan& P = *reinterpret_cast<Plan*>(smem);
   float* lut = reinterpret_cast<float*>(smem + ((sizeof(Plan) + 15) & ~size_t(15)));
   float* eq_lut = lut + 256;
@@ -1316,45 +1695,29 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   T.b = T.a + L.ntab;
   T.c = T.b + L.ntab;
   uint8_t* tile = smem + L.off_tile;
-  uint8_t* rowbuf = smem + L.off_rowbuf + (size_t)warp * (cap + ROWBUF_SLACK);
-  int2* dtab = reinterpret_cast<int2*>(smem + L.off_dtab);
-  float* lab = reinterpret_cast<float*>(smem + L.off_lab);
   uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // cluster exchange barrier
 
-  trace_mark(a, 0);
-  if (a.trace_out && tid == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    a.trace_out[(size_t)blockIdx.x * 16 + 5] = smid;
+  trace_mark<TRACE>(a, 0);
+  if (TRACE) {
+    if (a.trace_out && tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      a.trace_out[(size_t)blockIdx.x * 16 + 5] = smid;
+    }
+  }
+  if (worker) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // plan_kernel is done (no-op without a programmatic launch)
+    canvas_worker(a, P, smem + L.off_tile, (TRACE && a.trace_out) ? a.trace_out + (size_t)blockIdx.x * 16 : nullptr);
+    return;
   }
   if (tid == 0) {
     mbar_init(xbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- label data of this sample -> shared memory (overlaps the plan; labels do not depend on it) ----------
-  int lab_total = 0;
-  for (int f = 0; f < a.n_fields; ++f) {
-    const B200AugField& F = a.fields[f];
-    if (F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4) lab_total += F.count * F.dim;
-  }
-  const bool lab_staged = lab_total <= LAB_CAP;
-  if (lab_staged) {
-    int off = 0;
-    for (int f = 0; f < a.n_fields; ++f) {
-      const B200AugField& F = a.fields[f];
-      if (!(F.in && F.out && F.category != B200AUG_CAT_GENERAL && F.dim <= 4)) continue;
-      const int n = F.count * F.dim;
-      const float* src = F.in + (size_t)b * n;
-      for (int i = tid; i < n; i += NTHREADS)  // asynchronous: the loads overlap the plan instead of stalling in front of it
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(lab + off + i)), "l"(src + i) : "memory");
-      off += n;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // ---- the plan: precomputed by plan_kernel (loaded with the staged labels' cp.async group) or built here -----------
-  const bool preplanned = a.plans != nullptr && lay_w == ow && lay_h == oh;
+  // ---- the plan: precomputed by plan_kernel or built here (the labels are plan_kernel's business either way) -----------
+  const bool preplanned = a.plans != nullptr;
   if (preplanned) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // plan_kernel (launched just before, overlapping our start) is done
+    if (dep_mode == 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // plan_kernel is done
     const unsigned char* rec = a.plans + (size_t)b * a.plan_stride;
     const int nv_plan = (int)(plan_bytes() >> 4), nv_tab = (int)(plan_tab_bytes(ow, oh) >> 4);
     for (int i = tid; i < nv_plan + nv_tab; i += NTHREADS) {
@@ -1362,13 +1725,13 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(rec + 16 * (size_t)i) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
-    build_plan(a, b, P, warp, lane, cr, reinterpret_cast<PlanCore*>(lut));  // (the LUT area is idle until the plan exists)
+    build_plan(a, b, P, warp, lane, false, reinterpret_cast<PlanCore*>(lut));  // (the LUT area is idle until the plan exists)
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the staged labels
   __syncthreads();
 
-  trace_mark(a, 1);
+  trace_mark<TRACE>(a, 1);
   // Samples whose photometric chain is a single point function (no equalize, blur or noise: more than half of the training
   // draws, and every evaluation sample) get their LUT now: the INTER_AREA pass can then write float32 output directly
   // (`direct` below).  The cluster barrier in front of the resampling orders these writes before their first use.
@@ -1391,53 +1754,43 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     if (tid == 0 && rx_bytes)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(xbar)), "r"(rx_bytes) : "memory");
   }
-  if (tid == 0 && a.status_out) a.status_out[b] = P.status;
-  // The labels only need the plan; they are transformed once the CTAs of the cluster no longer wait for each other (after the
-  // tile exchange), so that rank 0 does not hold its partner up in front of the resampling.
-  const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
-  if (!want_image) {
-    if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
-    return;
-  }
 
-  // ---- resize tables (unless they came with the precomputed plan), warp column tables ---------------------------------
+  // ---- resize tables (unless they came with the precomputed plan) -------------------------------------------------------
   const int rs = P.rs_mode;
-  if (!preplanned) build_tables(a, P, T, tid, lane);
-  trace_mark(a, 8);
-  const bool use_dtab = (P.src_mode == SRC_WARP) && (P.cw <= DT_CAP);
-  if (use_dtab) {
-    for (int x = tid; x < P.cw; x += NTHREADS)
-      dtab[x] = make_int2(rint_d2i(__dmul_rn(__dmul_rn(P.mi[0], (double)x), 1024.0)),
-                          rint_d2i(__dmul_rn(__dmul_rn(P.mi[3], (double)x), 1024.0)));
-  }
+  if (!preplanned) build_tables(a, P, T, tid, lane, NTHREADS);
+  trace_mark<TRACE>(a, 8);
   if (a.flags & B200AUG_F_PHOTOMETRIC) {
     hist8[tid] = 0;
     binhist[tid] = 0;
   }
-  trace_mark(a, 7);
-  cluster_sync(cl);  // (also: every CTA of the cluster is running before any distributed-shared-memory access)
-
-  trace_mark(a, 2);
-  // ---- rotated samples, stage 1: warpAffine into this sample's scratch canvas; stage 2 is then a plain crop of it ----
-  if (use_dtab && a.workspace && P.status == B200AUG_S_OK) {
-    const int spitch = (P.cw + 16 + 15) & ~15;  // 16-byte aligned rows with room for the bulk copies' over-read
-    if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
-      uint8_t* scratch = a.workspace + (size_t)b * a.workspace_stride;
-      warp_canvas_to_scratch(P, dtab, rowbuf, cap + ROWBUF_SLACK, scratch, spitch, warp, lane, cr, cl);
-      cluster_sync(cl);  // the tiles were produced by all CTAs of the cluster
-      if (tid == 0) {
-        P.src = scratch;
-        P.pitch = spitch;
-        P.sw = spitch;  // columns [cw, spitch) are padding the row copies may touch but no tap ever reads
-        P.sh = P.ch + 1;
-        P.x0 = 0;
-        P.y0 = 0;
-        P.src_mode = SRC_CROP;
+  // ---- rotated samples: the canvas workers leave the cv2.warpAffine canvas in the workspace; from here on the sample is a
+  // plain crop of it (image_geometric_cv2.py:121-134: warpAffine at source resolution, then cv2.resize)
+  if (P.src_mode == SRC_WARP && P.cv_ptr != nullptr) {
+    if (tid == 0) {
+      const uint32_t* done = plan_tail(a.plans, a.batch, a.plan_stride).done + b;
+      uint32_t v;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
+        if (v >= (uint32_t)WK_CHUNKS) break;
+        __nanosleep(256);
       }
-      __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      P.src = P.cv_ptr;
+      P.pitch = P.cv_pitch;
+      P.sw = P.cv_pitch;  // columns [cw, pitch) are padding the row copies may touch but no tap ever reads
+      P.sh = P.ch + 1;
+      P.x0 = 0;
+      P.y0 = 0;
+      P.src_mode = SRC_CROP;
     }
   }
-  trace_mark(a, 6);
+  trace_mark<TRACE>(a, 7);
+  __syncthreads();
+
+  trace_mark<TRACE>(a, 2);
+  trace_mark<TRACE>(a, 6);
   // ---- resample into the uint8 tile -----------------------------------------------------------------------
   const TileMap tm = make_tile_map(P, ow, oh);
   // columns [0, ow_band) are resampled by the warps' bands, a short last group by the per-pixel path
@@ -1462,14 +1815,14 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   }
   // direct: no tile, no exchange, no output pass -- the resampling pass writes the float32 crop itself
   const bool direct = fast && lut_early && rs == RS_AREA && P.fin == 0 && P.rot_dir == 0;
+  // Every CTA of the cluster must be running (its exchange barrier initialised) before the tile exchange touches its shared
+  // memory: arrive now, wait only in front of the exchange -- the resampling in between never waits for the partner.
+  // (direct samples have no exchange; `direct` comes out the same in all CTAs of the cluster.)
+  if (cl > 1 && !direct) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   if (fast) {
     const int kx = P.kx;
     float* const gimg = direct ? a.image_f32_out + (size_t)b * npix : nullptr;
-#define B200AUG_BAND(KK)                                                              \
-  do {                                                                                \
-    if (direct) area_band<KK, true>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg); \
-    else area_band<KK, false>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, nullptr);  \
-  } while (0)
+#define B200AUG_BAND(KK) area_band<KK>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg)
     if (kx <= 3) B200AUG_BAND(3);
     else if (kx == 4) B200AUG_BAND(4);
     else B200AUG_BAND(6);
@@ -1544,16 +1897,16 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     for (int p = tid; p < npix; p += NTHREADS) tile[p] = 0;
   }
   if (direct) {  // the crop is already in global memory; only the labels are left (both CTAs of the cluster take this exit)
-    trace_mark(a, 3);
-    if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
-    trace_mark(a, 9);
-    trace_mark(a, 4);
+    trace_mark<TRACE>(a, 3);
+    trace_mark<TRACE>(a, 9);
+    trace_mark<TRACE>(a, 4);
     return;
   }
   // ---- cluster exchange: every CTA resampled a band of rows into its own tile; now each sends its band to the others.
   // Without a 90-degree rotation the band is a contiguous byte range of the tile: its 16-byte aligned interior goes as
   // one bulk copy through distributed shared memory (completing on the receiver's mbarrier), the ragged ends as byte
   // stores.  Rotated-by-90 samples (1 %) send pixel by pixel.
+  if (cl > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (cl > 1 && P.status == B200AUG_S_OK) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tile writes (generic proxy) before the bulk copy reads them
     __syncthreads();
@@ -1583,15 +1936,14 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     if (rx_bytes) mbar_wait(xbar32, 0);  // the other CTAs' bands have landed in this tile
   }
   cluster_sync(cl);  // every CTA's tile now holds the whole crop; no distributed-shared-memory access after this point
-  trace_mark(a, 3);
-  if (cr == 0) transform_labels(a, P, b, lab_staged ? lab : nullptr);
-  trace_mark(a, 9);
+  trace_mark<TRACE>(a, 3);
+  trace_mark<TRACE>(a, 9);
 
   // ---- uint8 output (geometric stages only) --------------------------------------------------------------
   if (!(a.flags & B200AUG_F_NORMALIZE)) {
     uint8_t* out = a.image_u8_out + (size_t)b * npix;
     for (int p = ((cr * npix) >> cs) + tid; p < (((cr + 1) * npix) >> cs); p += NTHREADS) out[p] = tile[p];
-    trace_mark(a, 4);
+    trace_mark<TRACE>(a, 4);
     return;
   }
 
@@ -1673,7 +2025,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     __syncthreads();
   }
 
-  trace_mark(a, 10);
+  trace_mark<TRACE>(a, 10);
   // ---- output pass ----------------------------------------------------------------------------------------
   float* out = a.image_f32_out + (size_t)b * npix;
   const int Q = (npix + 3) >> 2;
@@ -1686,7 +2038,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
         if (p < npix) out[p] = lut[tile[p]];
       }
     }
-    trace_mark(a, 4);
+    trace_mark<TRACE>(a, 4);
     return;
   }
   const uint64_t sid = a.photo.sample_offset + (uint64_t)b;
@@ -1784,7 +2136,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
       }
     }
   }
-  trace_mark(a, 4);
+  trace_mark<TRACE>(a, 4);
 }
 
 
@@ -2102,6 +2454,11 @@ extern "C" int64_t b200aug_plan_stride(int out_w, int out_h) {
   return (int64_t)(plan_bytes() + plan_tab_bytes(out_w, out_h));
 }
 
+extern "C" int64_t b200aug_plan_buffer_bytes(int batch, int out_w, int out_h) {
+  if (batch < 0 || out_w <= 0 || out_h <= 0) return 0;
+  return (int64_t)batch * b200aug_plan_stride(out_w, out_h) + (int64_t)plan_tail_bytes(batch);
+}
+
 extern "C" int64_t b200aug_workspace_stride(int max_side) {
   if (max_side <= 0) return 0;
   const int64_t spitch = (max_side + 16 + 15) & ~15;
@@ -2185,33 +2542,76 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   int cap = a.rowbuf_capacity > 0 ? a.rowbuf_capacity : DEFAULT_ROWBUF;
   cap = (cap + 15) & ~15;
   const bool want_image = (a.flags & B200AUG_F_NORMALIZE) ? (a.image_f32_out != nullptr) : (a.image_u8_out != nullptr);
-  const int lay_w = want_image ? a.out_w : 1, lay_h = want_image ? a.out_h : 1;
-  const size_t smem = smem_layout(lay_w, lay_h, cap).total;
-  if (smem > 227 * 1024) return B200AUG_E_SMEM;
-  cudaError_t e = cudaFuncSetAttribute(fused_augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  auto fail = [&](cudaError_t err) { g_last_cuda_error = (int)err; return B200AUG_E_CUDA; };
   KArgs K;
   K.a = a;
   int cl = a.cluster_size > 0 ? a.cluster_size : DEFAULT_CLUSTER;
-  if (cl != 1 && cl != 2 && cl != 4) return B200AUG_E_INVALID_ARG;
+  if (cl != 1 && cl != 2 && cl != 4 && cl != 8) return B200AUG_E_INVALID_ARG;
+
+  // ---- kernel 1: plans, resize tables and labels of every sample (one small CTA each).  The record of a sample goes to
+  // a.plans when the caller provides that scratch; otherwise the fused kernel rebuilds the plan for itself.
+  const size_t rec = plan_bytes() + plan_tab_bytes(a.out_w, a.out_h);
+  const bool records = want_image && a.plans != nullptr && rec <= 48 * 1024;  // (very large outputs: tables built in the fused kernel)
   if (a.plans && want_image) {
-    const size_t rec = plan_bytes() + plan_tab_bytes(a.out_w, a.out_h);
     if (a.plan_stride < (int64_t)rec || (a.plan_stride & 15) || (reinterpret_cast<uintptr_t>(a.plans) & 15)) return B200AUG_E_INVALID_ARG;
-    if (rec > 48 * 1024) {
-      K.a.plans = nullptr;  // (very large outputs: the tables are built inside the fused kernel)
-    } else {
-      plan_kernel<<<a.batch, NTHREADS, rec + ((sizeof(PlanCore) + 15) & ~size_t(15)), (cudaStream_t)stream>>>(K);
-      e = cudaGetLastError();
-      if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
-    }
-  } else {
-    K.a.plans = nullptr;
   }
+  if (!records) K.a.plans = nullptr;
+  // canvas workers: the first warp_ctas CTAs of the fused grid (a multiple of the cluster size); none without records +
+  // workspace + a rotation parameter (rotated samples then take the per-pixel path)
+  static thread_local int attr_dev = -1;     // per host thread and device: function attributes, SM count
+  static thread_local int attr_smem = 0, n_sm = 0;
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(e);
+  if (dev != attr_dev) {
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(e);
+  }
+  {
+    int w = 0;
+    if (records && a.workspace && (a.flags & B200AUG_F_FOCUS) && a.angles && a.warp_ctas >= 0)
+      w = (a.warp_ctas > 0) ? a.warp_ctas : (3 * n_sm) / 2;
+    K.a.warp_ctas = (w + cl - 1) / cl * cl;
+  }
+  if (a.phase < B200AUG_PHASE_ALL || a.phase > B200AUG_PHASE_MAIN) return B200AUG_E_INVALID_ARG;
+  if (a.phase == B200AUG_PHASE_MAIN && !records) return B200AUG_E_INVALID_ARG;  // nothing to pick the plans up from
+  if (a.phase != B200AUG_PHASE_MAIN) {
+    const size_t psmem = plan_bytes() + (records ? plan_tab_bytes(a.out_w, a.out_h) : 0) + ((sizeof(PlanCore) + 15) & ~size_t(15));
+    plan_kernel<<<a.batch, NTHREADS, psmem, st>>>(K, records ? 1 : 0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e);
+  }
+  if (!want_image || a.phase == B200AUG_PHASE_PLAN) return B200AUG_OK;  // label-only call / plan phase
+
+  const size_t smem = smem_layout(a.out_w, a.out_h, cap).total;
+  if (smem > 227 * 1024) return B200AUG_E_SMEM;
+  if (dev != attr_dev || (int)smem > attr_smem) {
+    e = cudaFuncSetAttribute(fused_augment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_augment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static const int carve = getenv("B200AUG_CARVEOUT") ? atoi(getenv("B200AUG_CARVEOUT")) : -1;
+    if (carve >= 0) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_augment_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_augment_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+    if (e != cudaSuccess) return fail(e);
+    attr_dev = dev;
+    attr_smem = (int)smem;
+  }
+
+  const int dep_mode = (records && a.phase == B200AUG_PHASE_ALL) ? 1 : 0;  // (MAIN alone: plain stream / event order)
+  cudaLaunchAttribute pdl;
+  pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl.val.programmaticStreamSerializationAllowed = 1;
+
+  // ---- kernel 2: canvas workers + one cluster per sample (resampling, photometric chain)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)a.batch * cl);
+  cfg.gridDim = dim3((unsigned)(K.a.warp_ctas + a.batch * cl));
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
+  cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
@@ -2219,14 +2619,14 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (K.a.plans) {  // start while plan_kernel drains (the kernel waits with griddepcontrol.wait before reading the plans)
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+  if (dep_mode != 0) {  // start while the kernel in front drains (see fused_augment_kernel: dep_mode)
+    attr[1] = pdl;
     cfg.numAttrs = 2;
   }
-  e = cudaLaunchKernelEx(&cfg, fused_augment_kernel, K, cap, lay_w, lay_h);
+  if (a.trace_out) e = cudaLaunchKernelEx(&cfg, fused_augment_kernel<true>, K, cap, dep_mode);
+  else e = cudaLaunchKernelEx(&cfg, fused_augment_kernel<false>, K, cap, dep_mode);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  if (e != cudaSuccess) return fail(e);
   return B200AUG_OK;
 }
 

@@ -6,13 +6,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200aug.so")
+LIB_PATH = os.environ.get("B200AUG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libb200aug.so")  # (env: experiment builds)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_FIELDS, NUM_OPS, NUM_NOISE = 8, 6, 4
 
 F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN = 1, 2, 4, 8, 16, 32, 64
 CAT_GENERAL, CAT_QUAT, CAT_XYS, CAT_ROI, CAT_POINTS = 0, 1, 2, 3, 4
+PHASE_ALL, PHASE_PLAN, PHASE_MAIN = 0, 1, 2
 S_OK, S_EMPTY_BOX, S_UNSUPPORTED, S_ROWBUF = 0, 1, 2, 3
 OP_EQUALIZE, OP_POSTERIZE, OP_GAMMA, OP_CONTRAST, OP_BRIGHTNESS, OP_BLUR = range(6)
 
@@ -44,12 +45,12 @@ class FusedArgs(C.Structure):
                 ("view_roi_out", C.c_void_p), ("tr_out", C.c_void_p), ("backtransform_out", C.c_void_p),
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),
                 ("trace_out", C.c_void_p), ("order", C.c_void_p), ("workspace", C.c_void_p), ("workspace_stride", C.c_int64),
-                ("plans", C.c_void_p), ("plan_stride", C.c_int64),
+                ("plans", C.c_void_p), ("plan_stride", C.c_int64), ("warp_ctas", C.c_int32), ("phase", C.c_int32),
                 ("photo", PhotoParams)]
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
+           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
            "b200aug_quat_matrix", "b200aug_jpeg_info", "b200aug_decode_jpeg_gray", "b200aug_jpeg_last_status")
 
 
@@ -72,6 +73,8 @@ def _load():
     lib.b200aug_workspace_stride.argtypes = [C.c_int]
     lib.b200aug_plan_stride.restype = C.c_int64
     lib.b200aug_plan_stride.argtypes = [C.c_int, C.c_int]
+    lib.b200aug_plan_buffer_bytes.restype = C.c_int64
+    lib.b200aug_plan_buffer_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.b200aug_upload_row_bands.restype = C.c_int
     lib.b200aug_upload_row_bands.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200aug_fused_forward.restype = C.c_int

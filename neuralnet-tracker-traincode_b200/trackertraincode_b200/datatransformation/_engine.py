@@ -6,6 +6,7 @@ arithmetic of the path lives in csrc/.  No CPU fallback exists: tensors must be 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -71,11 +72,23 @@ class PreparedCall:
     def __init__(self, args, device, result: FusedResult, keep):
         self.args, self.device, self.result, self._keep = args, device, result, keep
 
-    def launch(self, stream: Optional[int] = None) -> FusedResult:
+    def launch(self, stream: Optional[int] = None, phase: int = N.PHASE_ALL) -> FusedResult:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.args.phase = phase
         N.check(N.lib.b200aug_fused_forward(C.byref(self.args), C.c_void_p(stream)), "b200aug_fused_forward")
         return self.result
+
+    def launch_plan(self, stream: Optional[int] = None) -> None:
+        """Phase 1 alone (plan_kernel: plans, resize tables, labels, side outputs).  A loop that pipelines steps runs this
+        for step s + 1 on a second stream while `launch_main` of step s is still at work; the call must have been prepared
+        with `private_scratch=True` so that its plan records are not another call's."""
+        self.launch(stream, N.PHASE_PLAN)
+
+    def launch_main(self, stream: Optional[int] = None) -> FusedResult:
+        """Phase 2 alone (canvas workers + resampling + photometric chain), after `launch_plan` has completed (event order is
+        the caller's business)."""
+        return self.launch(stream, N.PHASE_MAIN)
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -188,33 +201,48 @@ _PLAN_BUFFERS: Dict[Any, torch.Tensor] = {}
 def _plan_buffer(device, B: int, ow: int, oh: int):
     """Scratch for the plans + resize tables of one launch (B200AugFusedArgs.plans), cached like the canvas workspace."""
     stride = int(N.lib.b200aug_plan_stride(ow, oh))
+    nbytes = int(N.lib.b200aug_plan_buffer_bytes(B, ow, oh))  # B records + the tail (work counters, per-sample flags)
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _PLAN_BUFFERS.get(key)
-    if buf is None or buf.numel() < B * stride:
-        buf = torch.empty(B * stride, dtype=torch.uint8, device=device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _PLAN_BUFFERS[key] = buf
     return buf, stride
 
 
+FIRST_WAVE_SAMPLES = 148  # sample clusters (2 CTAs) next to the canvas workers in the first wave of a 148-SM part
+
+
 def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams]) -> Optional[torch.Tensor]:
-    """Most expensive samples first (B200AugFusedArgs.order).  Only parameters that are still on the host are looked at
-    -- this never synchronises with the device; returns None when nothing distinguishes the samples."""
+    """Launch order of the fused kernel's clusters (B200AugFusedArgs.order): most expensive photometric chains first, but
+    no rotated sample in the first wave -- their canvases come from the canvas workers, which start with the first wave
+    and walk the rotated samples in this same order.  Only parameters that are still on the host are looked at -- this never
+    synchronises with the device; returns None when nothing distinguishes the samples."""
     cost = torch.zeros(B)
     known = False
-    if geo is not None and not geo.angles.is_cuda:
-        # relative to a plain crop (17.5 us per CTA in the r01g trace): warpAffine stage +34 us, blur +20, a noise stage +5
-        cost += (geo.angles.reshape(B) != 0).float() * 1.9  # warpAffine stage
-        known = True
     if photo is not None and not torch.as_tensor(photo.apply).is_cuda:
+        # relative to a plain crop (15 us per CTA in the r02 trace): blur +20 us, equalize +3, a noise stage +5
         ap = torch.as_tensor(photo.apply).reshape(B, N.NUM_OPS).bool()
         chosen = torch.zeros(N.NUM_OPS, dtype=torch.bool)
         chosen[list(photo.order)] = True
-        cost += (ap[:, 5] & chosen[5]).float() * 1.15 + (ap[:, 0] & chosen[0]).float() * 0.15
-        cost += torch.as_tensor(photo.noise_apply).reshape(B, N.NUM_NOISE).float().sum(1) * 0.3
+        cost += (ap[:, 5] & chosen[5]).float() * 1.3 + (ap[:, 0] & chosen[0]).float() * 0.2
+        cost += torch.as_tensor(photo.noise_apply).reshape(B, N.NUM_NOISE).float().sum(1) * 0.35
         known = True
-    if not known or float(cost.max()) == 0.0:
+    rot = None
+    if geo is not None and not geo.angles.is_cuda:
+        rot = geo.angles.reshape(B) != 0
+        known = known or bool(rot.any())
+    if not known or (float(cost.max()) == float(cost.min()) and (rot is None or not bool(rot.any()))):
         return None
-    return torch.argsort(cost, descending=True, stable=True).to(torch.int32)
+    order = torch.argsort(cost, descending=True, stable=True)
+    if rot is not None and bool(rot.any()):
+        # the first wave: the dearest unrotated samples; everything else by cost behind them
+        r = rot[order]
+        head = order[~r][:FIRST_WAVE_SAMPLES]
+        taken = torch.zeros(B, dtype=torch.bool)
+        taken[head] = True
+        order = torch.cat([head, order[~taken[order]]])
+    return order.to(torch.int32)
 
 
 def marshal_photo(photo: PhotoParams, B: int, device) -> Tuple[Any, List[Any]]:
@@ -251,7 +279,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
                   want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0,
-                  schedule: bool = True, preplan: bool = True) -> PreparedCall:
+                  schedule: bool = True, preplan: bool = True, private_scratch: bool = False) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -275,6 +303,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     args.beyond_border_shift = beyond_border_shift
     args.roi_field = args.landmark_field = -1
     args.cluster_size = cluster_size
+    args.warp_ctas = int(os.environ.get("B200AUG_WARP_CTAS", "0"))  # experiment knob, 0 = library default
     keep: List[Any] = []
     out_data: Dict[str, Any] = {}
 
@@ -380,7 +409,11 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         args.workspace, args.workspace_stride = ws.data_ptr(), stride
         keep.append(ws)
     if image_keys and preplan:
-        pb, pstride = _plan_buffer(device, B, ow, oh)
+        if private_scratch:  # this call's own plan records (its plan phase may overlap another call's main phase)
+            pstride = int(N.lib.b200aug_plan_stride(ow, oh))
+            pb = torch.empty(int(N.lib.b200aug_plan_buffer_bytes(B, ow, oh)), dtype=torch.uint8, device=device)
+        else:
+            pb, pstride = _plan_buffer(device, B, ow, oh)
         args.plans, args.plan_stride = pb.data_ptr(), pstride
         keep.append(pb)
     if flags & N.F_FOCUS:
@@ -397,7 +430,8 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         args.status_out = status.data_ptr()
     trace = None
     if want_trace:  # per-CTA timeline (profiling aid, see include/b200aug.h: trace_out)
-        trace = torch.zeros((B * (cluster_size or 2), 16), dtype=torch.int64, device=device)
+        # B * cluster_size CTAs of the fused kernel, then up to 1024 CTAs of warp_kernel
+        trace = torch.zeros((B * (cluster_size or 2) + 1024, 16), dtype=torch.int64, device=device)
         args.trace_out = trace.data_ptr()
 
     # ---- assemble the result (tensors are written when the call is launched)

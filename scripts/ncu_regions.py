@@ -4,7 +4,7 @@ import re,csv,collections,sys
 csv.field_size_limit(10**9)
 dis,sasscsv,srcf=sys.argv[1],sys.argv[2],sys.argv[3]
 lines=open(dis).read().split('\n')
-start=[i for i,l in enumerate(lines) if l.startswith('.text._ZN7b200aug20fused_augment_kernel')][0]
+start=[i for i,l in enumerate(lines) if l.startswith('.text._ZN7b200aug20fused_augment_kernelILb0E')][0]
 cur=None; ins=[]
 for l in lines[start+1:]:
     if (l.startswith('.text.') or l.startswith('//-----')) and ins: break

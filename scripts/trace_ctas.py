@@ -35,8 +35,18 @@ for _ in range(5):
 torch.cuda.synchronize()
 t = call.result.trace.cpu().numpy().astype(np.int64)
 CL = int(os.environ.get("B200AUG_CLUSTER", "0")) or 2
-t = t[: bench.BATCH * CL]
-t0 = t[:, 0].min()
+live = t[:, 0] > 0
+is_worker = live & (t[:, 1] == 0)  # canvas workers (the first CTAs of the grid) never mark "plan loaded"
+tw = t[is_worker]
+t = t[live & ~is_worker][: bench.BATCH * CL]
+t0 = min(t[:, 0].min(), tw[:, 0].min()) if len(tw) else t[:, 0].min()
+if len(tw):
+    print(f"canvas workers: {len(tw)} CTAs on {len(np.unique(tw[:, 5]))} SMs; start {(tw[:, 0].min() - t0) / 1e3:.1f}..{(tw[:, 0].max() - t0) / 1e3:.1f} us, "
+          f"end {(tw[:, 4].min() - t0) / 1e3:.1f}..{(tw[:, 4].max() - t0) / 1e3:.1f}; items per CTA {tw[:, 2].min()}..{tw[:, 2].max()} (total {tw[:, 2].sum()})")
+if len(tw):
+    nt = max(int(tw[:, 12].sum()), 1)
+    print("canvas workers, cycles per tile (thread 0): issue %.0f wait %.0f gather %.0f describe+barrier %.0f; tiles %d; total CTA-us %.0f" % (
+        tw[:, 8].sum() / nt, tw[:, 9].sum() / nt, tw[:, 10].sum() / nt, tw[:, 11].sum() / nt, nt, (tw[:, 4] - tw[:, 0]).sum() / 1e3))
 start, plan, tabs, res, end, smid = (t[:, i] - (t0 if i < 5 else 0) for i in range(6))
 print(f"kernel span {(end.max()) / 1e3:.1f} us; CTA duration us: mean {np.mean(end - start) / 1e3:.1f} median {np.median(end - start) / 1e3:.1f} "
       f"p95 {np.percentile(end - start, 95) / 1e3:.1f} max {(end - start).max() / 1e3:.1f}")
@@ -48,12 +58,15 @@ eq = np.repeat((pp.apply[:, 0] & (0 in list(pp.order)))[samp].astype(bool), CL)
 noise = np.repeat(pp.noise_apply.any(1)[samp], CL)
 warp_stage = t[:, 6] - t0 - tabs
 m6, m7, m8, m9, m10 = (t[:, i] - t0 for i in (6, 7, 8, 9, 10))
-ph = {"plan": plan - start, "tab": m8 - plan, "dtab..": m7 - m8, "csync": tabs - m7, "warp": m6 - tabs, "area+xchg": res - m6, "labels": m9 - res,
+ph = {"plan": plan - start, "tab": m8 - plan, "cv_wait": m7 - m8, "csync": tabs - m7, "warp": m6 - tabs, "area+xchg": res - m6, "labels": m9 - res,
       "lut": np.where(m10 > 0, m10 - m9, 0), "output": np.where(m10 > 0, end - m10, end - m9), "total": end - start}
 for name, m in (("all", np.ones_like(rot)), ("unrotated", ~rot), ("rotated", rot), ("blur", blur), ("equalize", eq), ("noise", noise),
                 ("plain(no rot/photo)", ~rot & ~blur & ~eq & ~noise)):
     if m.sum():
         print(f"{name:22s} n={int(m.sum()):4d} " + " ".join(f"{k}={np.mean(v[m]) / 1e3:7.1f}" for k, v in ph.items()))
+early = start < 8e3
+print(f"first wave: {int(early.sum())} CTAs on {len(np.unique(smid[early]))} SMs, end times us: " + str(np.round(np.sort(end[early])[::8] / 1e3, 1).tolist()))
+print("starts (us) sorted, every 32nd:", np.round(np.sort(start)[::32] / 1e3, 1).tolist())
 print("start-time histogram (us):", np.histogram(start / 1e3, bins=10)[0].tolist(), "last start", start.max() / 1e3)
 busy = np.zeros(int(smid.max()) + 1)
 for s, a, e in zip(smid, start, end):

@@ -138,19 +138,28 @@ def test_kornia_container_descriptor_rules():
         FusedPoseAugmentation(129, roi_override="extent_to_forehead")
 
 
-def test_launch_order_puts_heavy_samples_first():
+def test_launch_order_first_wave_unrotated_then_by_cost():
+    """Rotated samples get their canvas from the canvas workers, which start with the first wave of the fused kernel: the
+    first wave holds the dearest unrotated samples, everything else follows by cost."""
     B = 8
     geo = E.GeoParams(torch.ones(B), torch.tensor([0, 0.5, 0, 0, 0, 0, -0.5, 0.0]), torch.zeros(B, 2))
     assert E.launch_order(B, E.GeoParams(torch.ones(B), torch.zeros(B), torch.zeros(B, 2)), None) is None
     o = E.launch_order(B, geo, None)
-    assert sorted(o.tolist()) == list(range(B)) and set(o[:2].tolist()) == {1, 6}
+    assert sorted(o.tolist()) == list(range(B)) and set(o[-2:].tolist()) == {1, 6}  # (all 6 unrotated fit the first wave)
     ph = draw_photo_params(B, 0, 0)
     ph.order, ph.apply = [5, 0, 2, 3], torch.zeros(B, 6, dtype=torch.bool)
-    ph.apply[3, 5] = True  # blurred: dearer than a plain crop, cheaper than a rotated one
-    ph.apply[6, 5] = True  # rotated and blurred: the most expensive of all
+    ph.apply[3, 5] = True  # blurred: the dearest unrotated sample
+    ph.apply[6, 5] = True  # rotated and blurred: first of the rotated ones
     ph.noise_apply = torch.zeros(B, 4, dtype=torch.bool)
     o = E.launch_order(B, geo, ph)
-    assert o[:3].tolist() == [6, 1, 3]
+    assert o[0].item() == 3 and o[-2:].tolist() == [6, 1]
+    old = E.FIRST_WAVE_SAMPLES
+    try:
+        E.FIRST_WAVE_SAMPLES = 2  # a first wave of two clusters: blurred + one plain, then the rotated blurred one
+        o = E.launch_order(B, geo, ph)
+        assert o[0].item() == 3 and o[2].item() == 6 and not {1, 6} & set(o[:2].tolist())
+    finally:
+        E.FIRST_WAVE_SAMPLES = old
 
 
 class _DS(torch.utils.data.Dataset):
