@@ -50,6 +50,8 @@ extern "C" {
 #define B200AUG_CAT_XYS 2         /* "xys" affinetrafo.py:89-95   transform_coord */
 #define B200AUG_CAT_ROI 3         /* "roi" affinetrafo.py:75-86   transform_roi */
 #define B200AUG_CAT_POINTS 4      /* "pts" affinetrafo.py:37-72   transform_keypoints (68-landmark flip_map) */
+#define B200AUG_CAT_BACKTRANSFORM 5 /* the "image_backtransform" entry (a [2,3] affine, count 1, dim 6): every transform tr
+                                     rewrites it as BT @ tr^-1, affinetrafo.py:137-147 */
 
 /* stage flags of b200aug_fused_forward, in pipeline order (trackertraincode/pipelines.py:372-383, 508-532) */
 #define B200AUG_F_HALF_PIXEL 0x01u         /* offset_points_by_half_pixel       batch/normalization.py:83-90 */
@@ -59,6 +61,9 @@ extern "C" {
 #define B200AUG_F_NORMALIZE 0x10u          /* normalize_batch                   batch/normalization.py:20-56 */
 #define B200AUG_F_PHOTOMETRIC 0x20u        /* KorniaImageDistortions x2         batch/intensity.py:30-64, pipelines.py:508-527 */
 #define B200AUG_F_WHITEN 0x40u             /* whiten_batch                      batch/normalization.py:94-99 */
+#define B200AUG_F_INSERT_BACKTRANSFORM 0x80u /* GeneralFocusRoi(insert_backtransform=True), batch/geometric.py:226-227: the
+                                              focus stage (re)starts the back-transform as tr^-1; later stages of the
+                                              same call compose onto it; written to backtransform_out */
 
 /* B200AugFusedArgs::phase */
 #define B200AUG_PHASE_ALL 0
@@ -87,7 +92,7 @@ typedef struct B200AugSrc {
 } B200AugSrc;
 
 /* One label tensor [B, count, dim] float32, transformed according to `category`. in == out is allowed for every
- * category except POINTS with count == 68 (the mirror permutation reads other rows). */
+ * category except POINTS with count == 68 (the mirror permutation reads other rows).  BACKTRANSFORM: count 1, dim 6. */
 typedef struct B200AugField {
   int32_t category;
   int32_t count;      /* items per sample (68 landmarks, 1 roi, ...) */
@@ -110,6 +115,8 @@ typedef struct B200AugPhotoParams {
   const float* brightness;      /* [B] */
   const uint8_t* noise_apply;   /* [B, 4] */
   float noise_std[B200AUG_NUM_NOISE];
+  int32_t noise_clip[B200AUG_NUM_NOISE]; /* RandomGaussianNoiseWithClipping (batch/intensity.py:43-53): clamp to [0,1] right behind
+                                   this stage, on the samples it was applied to */
   uint64_t seed;                /* Philox4x32-10 key */
   uint64_t sample_offset;       /* id of sample 0 in the noise stream (rank * local batch + step * global batch ...) */
 } B200AugPhotoParams;
@@ -132,6 +139,13 @@ typedef struct B200AugFusedArgs {
   const float* cos_sin;         /* optional [B,2]: host-evaluated torch.cos/sin(angles) (affine2d.py:46-47) */
   const float* translations;    /* [B,2] */
   float beyond_border_shift;    /* 0.3, geometric.py:104 */
+  /* explicit geometry instead of the sampled one (the tensor-level entries of tensors/image_geometric_cv2.py):
+   *   explicit_view_roi [B,4] int32: croprescale_image_cv2(img, roi, new_size) (:138-155) -- the integer box is cropped
+   *                     (zero padded) and resized; labels follow range_remap(box -> output);
+   *   explicit_tr [B,2,3]: affine_transform_image_cv2(img, tr, new_size) (:85-135) -- always the warpAffine path.
+   * With either one scales / angles / translations / the roi field are not read. */
+  const int32_t* explicit_view_roi;
+  const float* explicit_tr;
   /* horizontal_flip_and_rot_90 draws (batch/geometric.py:236-237) */
   const uint8_t* do_flip;       /* [B] or NULL */
   const int8_t* rot_dir;        /* [B] in {-1,0,1} or NULL */
@@ -146,7 +160,8 @@ typedef struct B200AugFusedArgs {
   /* outputs (each may be NULL) */
   int32_t* view_roi_out;        /* [B,4] rounded view box, geometric.py:205 */
   float* tr_out;                /* [B,2,3] focus transform, geometric.py:206-207 */
-  float* backtransform_out;     /* [B,2,3] tr^-1, geometric.py:226-227 */
+  float* backtransform_out;     /* [B,2,3] with F_INSERT_BACKTRANSFORM: tr^-1 of the focus stage (geometric.py:226-227) composed
+                                   with the inverse of every later stage of this call (affinetrafo.py:137-147) */
   uint8_t* image_u8_out;        /* [B,1,oh,ow] when F_NORMALIZE is not set */
   float* image_f32_out;         /* [B,1,oh,ow] when F_NORMALIZE is set */
   int32_t* status_out;          /* [B] B200AUG_S_* */

@@ -231,7 +231,8 @@ __device__ PlanCore plan_core(const B200AugFusedArgs& a, int b, const float box[
   c.rot_dir = (fliprot && a.rot_dir) ? (int)a.rot_dir[b] : 0;
   float f = 1.f, rx = 0.f, ry = 0.f, cs = 1.f, sn = 0.f;
   c.angle = 0.f;
-  if (focus) {
+  const bool sampled = focus && !a.explicit_view_roi && !a.explicit_tr;
+  if (sampled) {
     f = a.scales[b];
     rx = a.translations[2 * b];
     ry = a.translations[2 * b + 1];
@@ -245,28 +246,47 @@ __device__ PlanCore plan_core(const B200AugFusedArgs& a, int b, const float box[
   c.W = c.s.width;
   c.H = c.s.height;
   c.vx0 = c.vy0 = c.vx1 = c.vy1 = 0;
+  bool warp = false;
   if (focus) {
-    // GeneralFocusRoi._compute_view_roi, geometric.py:135-156 (float32 elementwise, op for op)
-    float bx0 = box[0], by0 = box[1], bx1 = box[2], by1 = box[3];
-    float bw = sub(bx1, bx0), bh = sub(by1, by0);
-    float cx = mul(0.5f, add(bx1, bx0)), cy = mul(0.5f, add(by1, by0));
-    float size = mul(fmaxf(bw, bh), f);
-    float bbs = a.beyond_border_shift;
-    float wx = add(mul(0.5f, fabsf(sub(size, bw))), mul(bbs, fminf(size, bw)));
-    float wy = add(mul(0.5f, fabsf(sub(size, bh))), mul(bbs, fminf(size, bh)));
-    float tx = mul(wx, rx), ty = mul(wy, ry);
-    float hs = mul(size, 0.5f);
-    // torch.round (half to even) -> int32, geometric.py:205
-    c.vx0 = (int)rintf(add(sub(cx, hs), tx)); c.vy0 = (int)rintf(add(sub(cy, hs), ty));
-    c.vx1 = (int)rintf(add(add(cx, hs), tx)); c.vy1 = (int)rintf(add(add(cy, hs), ty));
-    // geometric.py:159-178: tr = (denorm @ rot @ norm) @ range_remap(view -> [0,out])
-    Aff tr_roi = aff_range_remap((float)c.vx0, (float)c.vy0, (float)c.vx1, (float)c.vy1, 0.f, 0.f, (float)ow, (float)oh);
-    Aff nrm = aff_range_remap(0.f, 0.f, (float)ow, (float)oh, -1.f, -1.f, 1.f, 1.f);
-    Aff den = aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, (float)ow, (float)oh);
-    if (!a.cos_sin) cos_sin_rn(c.angle, cs, sn);
-    Aff rot = Aff{cs, -sn, 0.f, sn, cs, 0.f};
-    c.t1 = aff_compose(aff_compose(aff_compose(den, rot), nrm), tr_roi);
-    if (c.angle != 0.f) {
+    if (a.explicit_tr) {
+      // affine_transform_image_cv2(img, tr, new_size): the caller's transform, always through cv2.warpAffine
+      const float* m = a.explicit_tr + 6 * (size_t)b;
+      c.t1 = Aff{m[0], m[1], m[2], m[3], m[4], m[5]};
+      warp = true;
+    } else {
+      if (a.explicit_view_roi) {
+        // croprescale_image_cv2(img, roi, new_size): the caller's integer box
+        const int32_t* v = a.explicit_view_roi + 4 * (size_t)b;
+        c.vx0 = v[0]; c.vy0 = v[1]; c.vx1 = v[2]; c.vy1 = v[3];
+      } else {
+        // GeneralFocusRoi._compute_view_roi, geometric.py:135-156 (float32 elementwise, op for op)
+        float bx0 = box[0], by0 = box[1], bx1 = box[2], by1 = box[3];
+        float bw = sub(bx1, bx0), bh = sub(by1, by0);
+        float cx = mul(0.5f, add(bx1, bx0)), cy = mul(0.5f, add(by1, by0));
+        float size = mul(fmaxf(bw, bh), f);
+        float bbs = a.beyond_border_shift;
+        float wx = add(mul(0.5f, fabsf(sub(size, bw))), mul(bbs, fminf(size, bw)));
+        float wy = add(mul(0.5f, fabsf(sub(size, bh))), mul(bbs, fminf(size, bh)));
+        float tx = mul(wx, rx), ty = mul(wy, ry);
+        float hs = mul(size, 0.5f);
+        // torch.round (half to even) -> int32, geometric.py:205
+        c.vx0 = (int)rintf(add(sub(cx, hs), tx)); c.vy0 = (int)rintf(add(sub(cy, hs), ty));
+        c.vx1 = (int)rintf(add(add(cx, hs), tx)); c.vy1 = (int)rintf(add(add(cy, hs), ty));
+      }
+      // geometric.py:159-178: tr = (denorm @ rot @ norm) @ range_remap(view -> [0,out])
+      Aff tr_roi = aff_range_remap((float)c.vx0, (float)c.vy0, (float)c.vx1, (float)c.vy1, 0.f, 0.f, (float)ow, (float)oh);
+      if (a.explicit_view_roi) {
+        c.t1 = tr_roi;
+      } else {
+        Aff nrm = aff_range_remap(0.f, 0.f, (float)ow, (float)oh, -1.f, -1.f, 1.f, 1.f);
+        Aff den = aff_range_remap(-1.f, -1.f, 1.f, 1.f, 0.f, 0.f, (float)ow, (float)oh);
+        if (!a.cos_sin) cos_sin_rn(c.angle, cs, sn);
+        Aff rot = Aff{cs, -sn, 0.f, sn, cs, 0.f};
+        c.t1 = aff_compose(aff_compose(aff_compose(den, rot), nrm), tr_roi);
+      }
+      warp = c.angle != 0.f;
+    }
+    if (warp) {
       // affine_transform_image_cv2, image_geometric_cv2.py:85-135
       c.src_mode = SRC_WARP;
       double sf = (double)aff_scales(c.t1);
@@ -462,6 +482,19 @@ __device__ __noinline__ void transform_labels(const B200AugFusedArgs& a, const P
   for (int f = 0; f < a.n_fields; ++f) {
     const B200AugField& F = a.fields[f];
     if (!F.out || !F.in) continue;
+    if (F.category == B200AUG_CAT_BACKTRANSFORM) {
+      // "image_backtransform": BT @ tr^-1 for every stage of this call, in pipeline order (affinetrafo.py:137-147)
+      if (tl == 0) {
+        const float* in = F.in + (size_t)b * 6;
+        Aff bt = Aff{in[0], in[1], in[2], in[3], in[4], in[5]};
+        if (a.flags & B200AUG_F_FOCUS) bt = aff_compose(bt, aff_inv(P.t1.m));
+        if ((a.flags & B200AUG_F_FLIPROT) && P.has_t2) bt = aff_compose(bt, aff_inv(P.t2.m));
+        if (a.flags & B200AUG_F_NORMALIZE) bt = aff_compose(bt, aff_inv(P.t3.m));
+        float* out = F.out + (size_t)b * 6;
+        out[0] = bt.a00; out[1] = bt.a01; out[2] = bt.a02; out[3] = bt.a10; out[4] = bt.a11; out[5] = bt.a12;
+      }
+      continue;
+    }
     if (F.category == B200AUG_CAT_GENERAL || F.dim > 4) {
       const float* in = F.in + (size_t)b * F.count * F.dim;
       float* out = F.out + (size_t)b * F.count * F.dim;
@@ -476,7 +509,7 @@ __device__ __noinline__ void transform_labels(const B200AugFusedArgs& a, const P
     int f = 0, i = t;
     for (; f < a.n_fields; ++f) {
       const B200AugField& F = a.fields[f];
-      if (!F.out || !F.in || F.category == B200AUG_CAT_GENERAL || F.dim > 4) continue;
+      if (!F.out || !F.in || F.category == B200AUG_CAT_GENERAL || F.category == B200AUG_CAT_BACKTRANSFORM || F.dim > 4) continue;
       if (i < F.count) break;
       i -= F.count;
     }
@@ -1183,11 +1216,6 @@ __device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Pla
             float* o = a.tr_out + 6 * (size_t)b;
             o[0] = c.t1.a00; o[1] = c.t1.a01; o[2] = c.t1.a02; o[3] = c.t1.a10; o[4] = c.t1.a11; o[5] = c.t1.a12;
           }
-          if (side_out && a.backtransform_out && focus) {
-            Aff iv = aff_inv(c.t1);
-            float* o = a.backtransform_out + 6 * (size_t)b;
-            o[0] = iv.a00; o[1] = iv.a01; o[2] = iv.a02; o[3] = iv.a10; o[4] = iv.a11; o[5] = iv.a12;
-          }
         }
         if (side_out && lm && a.roi_field >= 0 && a.fields[a.roi_field].out) {
           // landmarks mode: the roi label is regenerated from the transformed landmarks after the crop (pipelines.py:347-351)
@@ -1338,6 +1366,15 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
     }
     if (a.status_out) a.status_out[b] = P.status;
   }
+  if (tid == 32 && a.backtransform_out && (a.flags & B200AUG_F_FOCUS) && (a.flags & B200AUG_F_INSERT_BACKTRANSFORM)) {
+    // GeneralFocusRoi(insert_backtransform=True): tr^-1 of the focus stage (geometric.py:226-227), then BT @ tr^-1 for the
+    // stages behind it in this call (affinetrafo.py:137-147)
+    Aff bt = aff_inv(P.t1.m);
+    if ((a.flags & B200AUG_F_FLIPROT) && P.has_t2) bt = aff_compose(bt, aff_inv(P.t2.m));
+    if (a.flags & B200AUG_F_NORMALIZE) bt = aff_compose(bt, aff_inv(P.t3.m));
+    float* o = a.backtransform_out + 6 * (size_t)b;
+    o[0] = bt.a00; o[1] = bt.a01; o[2] = bt.a02; o[3] = bt.a10; o[4] = bt.a11; o[5] = bt.a12;
+  }
   // the labels (warps 5-7) next to the resize tables (warps 0-4): both only read the finished plan
   transform_labels(a, P, b, 5 * 32, 3 * 32);
   if (with_tables) {
@@ -1371,7 +1408,7 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
 // Staged layout (as warp_canvas_to_scratch): box row r lands at offset B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift
 // of row 0, pm = pitch mod 16, so that source pixel (iy, ix) sits at c0 + (iy - by0)(B + pm) + (ix - bx0): linear, no
 // per-row alignment fix-up in the gather; B is 96 or 112, whichever spreads one canvas row's taps over more banks.
-constexpr int WK_CHUNKS = 2;                 // work items per rotated sample
+constexpr int WK_CHUNKS = 4;                 // work items per rotated sample
 constexpr int WK_NSTAGE = 3;                 // staged tiles in flight per worker
 constexpr int WT2_W = 64, WT2_H = 32;        // canvas tile of one pipeline step
 constexpr int WT2_ROWS = 74;                 // tallest staged bounding box
@@ -2116,13 +2153,16 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
 #pragma unroll
       for (int s = 0; s < B200AUG_NUM_NOISE; ++s) {
         if (!P.noise_on[s]) continue;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)s, (uint32_t)sid, 0x6E6F6973u), key);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)s, (uint32_t)sid, 0x6E6F6973u ^ (uint32_t)(sid >> 32)), key);
         float z[4];
         box_muller(r.x, r.y, z[0], z[1]);
         box_muller(r.z, r.w, z[2], z[3]);
         const float sd = a.photo.noise_std[s];
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = __fadd_rn(x[i], __fmul_rn(sd, z[i]));
+        if (a.photo.noise_clip[s])  // RandomGaussianNoiseWithClipping
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[i] = fminf(fmaxf(x[i], 0.f), 1.f);
       }
     }
 #pragma unroll
@@ -2250,12 +2290,16 @@ __global__ void __launch_bounds__(NTHREADS) photometric_f32_kernel(const float* 
 #pragma unroll
       for (int s = 0; s < B200AUG_NUM_NOISE; ++s) {
         if (!P.noise_on[s]) continue;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)s, (uint32_t)sid, 0x6E6F6973u), key);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)s, (uint32_t)sid, 0x6E6F6973u ^ (uint32_t)(sid >> 32)), key);
         float z[4];
         box_muller(r.x, r.y, z[0], z[1]);
         box_muller(r.z, r.w, z[2], z[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = __fadd_rn(x[i], __fmul_rn(pp.noise_std[s], z[i]));
+        if (pp.noise_clip[s])  // RandomGaussianNoiseWithClipping (torch.clip keeps a NaN)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (x[i] == x[i]) x[i] = fminf(fmaxf(x[i], 0.f), 1.f);
       }
     }
 #pragma unroll
@@ -2289,6 +2333,13 @@ __global__ void apply_affine2d_kernel(const float* __restrict__ tr, int64_t tr_s
     const int dim = F.dim, cnt = F.count;
     const float* in = F.in + (size_t)b * cnt * dim;
     float* out = F.out + (size_t)b * cnt * dim;
+    if (F.category == B200AUG_CAT_BACKTRANSFORM) {  // BT @ tr^-1, affinetrafo.py:137-147
+      if (threadIdx.x == 0) {
+        const Aff bt = aff_compose(Aff{in[0], in[1], in[2], in[3], in[4], in[5]}, aff_inv(D.m));
+        out[0] = bt.a00; out[1] = bt.a01; out[2] = bt.a02; out[3] = bt.a10; out[4] = bt.a11; out[5] = bt.a12;
+      }
+      continue;
+    }
     if (F.category == B200AUG_CAT_GENERAL || dim > 4) {
       if (in != out)
         for (int i = threadIdx.x; i < cnt * dim; i += blockDim.x) out[i] = in[i];
@@ -2509,6 +2560,7 @@ static int check_fields(int n, const B200AugField* f) {
     if (c == B200AUG_CAT_XYS && d != 3) return B200AUG_E_INVALID_ARG;
     if (c == B200AUG_CAT_ROI && d != 4) return B200AUG_E_INVALID_ARG;
     if (c == B200AUG_CAT_POINTS && d != 2 && d != 3) return B200AUG_E_INVALID_ARG;
+    if (c == B200AUG_CAT_BACKTRANSFORM && (d != 6 || f[i].count != 1)) return B200AUG_E_INVALID_ARG;
     if (c == B200AUG_CAT_POINTS && f[i].count == 68 && f[i].in == f[i].out) return B200AUG_E_INVALID_ARG;
   }
   return B200AUG_OK;
@@ -2522,7 +2574,7 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   if (!a.src_table && !a.src_uniform.ptr && (a.image_u8_out || a.image_f32_out)) return B200AUG_E_INVALID_ARG;
   int rc = check_fields(a.n_fields, a.fields);
   if (rc) return rc;
-  if (a.flags & B200AUG_F_FOCUS) {
+  if ((a.flags & B200AUG_F_FOCUS) && !a.explicit_view_roi && !a.explicit_tr) {
     if (!a.scales || !a.translations) return B200AUG_E_INVALID_ARG;
     const bool lm = (a.flags & B200AUG_F_ROI_FROM_LANDMARKS) != 0;
     if (lm && (a.landmark_field < 0 || a.landmark_field >= a.n_fields)) return B200AUG_E_INVALID_ARG;
@@ -2571,7 +2623,7 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   }
   {
     int w = 0;
-    if (records && a.workspace && (a.flags & B200AUG_F_FOCUS) && a.angles && a.warp_ctas >= 0)
+    if (records && a.workspace && (a.flags & B200AUG_F_FOCUS) && (a.angles || a.explicit_tr) && !a.explicit_view_roi && a.warp_ctas >= 0)
       w = (a.warp_ctas > 0) ? a.warp_ctas : (3 * n_sm) / 2;
     K.a.warp_ctas = (w + cl - 1) / cl * cl;
   }

@@ -11,8 +11,8 @@ LIB_PATH = os.environ.get("B200AUG_LIB") or os.path.join(os.path.dirname(_HERE),
 ABI_VERSION = 6
 MAX_FIELDS, NUM_OPS, NUM_NOISE = 8, 6, 4
 
-F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN = 1, 2, 4, 8, 16, 32, 64
-CAT_GENERAL, CAT_QUAT, CAT_XYS, CAT_ROI, CAT_POINTS = 0, 1, 2, 3, 4
+F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN, F_INSERT_BACKTRANSFORM = 1, 2, 4, 8, 16, 32, 64, 128
+CAT_GENERAL, CAT_QUAT, CAT_XYS, CAT_ROI, CAT_POINTS, CAT_BACKTRANSFORM = 0, 1, 2, 3, 4, 5
 PHASE_ALL, PHASE_PLAN, PHASE_MAIN = 0, 1, 2
 S_OK, S_EMPTY_BOX, S_UNSUPPORTED, S_ROWBUF = 0, 1, 2, 3
 OP_EQUALIZE, OP_POSTERIZE, OP_GAMMA, OP_CONTRAST, OP_BRIGHTNESS, OP_BLUR = range(6)
@@ -30,7 +30,7 @@ class Field(C.Structure):
 class PhotoParams(C.Structure):
     _fields_ = [("n_order", C.c_int32), ("order", C.c_int32 * NUM_OPS), ("clip", C.c_int32),
                 ("apply", C.c_void_p), ("bits", C.c_void_p), ("gamma", C.c_void_p), ("contrast", C.c_void_p),
-                ("brightness", C.c_void_p), ("noise_apply", C.c_void_p), ("noise_std", C.c_float * NUM_NOISE),
+                ("brightness", C.c_void_p), ("noise_apply", C.c_void_p), ("noise_std", C.c_float * NUM_NOISE), ("noise_clip", C.c_int32 * NUM_NOISE),
                 ("seed", C.c_uint64), ("sample_offset", C.c_uint64)]
 
 
@@ -39,7 +39,7 @@ class FusedArgs(C.Structure):
                 ("flags", C.c_uint32), ("rowbuf_capacity", C.c_int32),
                 ("src_table", C.c_void_p), ("src_uniform", Src), ("src_stride", C.c_int64),
                 ("scales", C.c_void_p), ("angles", C.c_void_p), ("cos_sin", C.c_void_p), ("translations", C.c_void_p),
-                ("beyond_border_shift", C.c_float), ("do_flip", C.c_void_p), ("rot_dir", C.c_void_p),
+                ("beyond_border_shift", C.c_float), ("explicit_view_roi", C.c_void_p), ("explicit_tr", C.c_void_p), ("do_flip", C.c_void_p), ("rot_dir", C.c_void_p),
                 ("n_fields", C.c_int32), ("roi_field", C.c_int32), ("landmark_field", C.c_int32), ("cluster_size", C.c_int32),
                 ("fields", Field * MAX_FIELDS),
                 ("view_roi_out", C.c_void_p), ("tr_out", C.c_void_p), ("backtransform_out", C.c_void_p),

@@ -53,6 +53,7 @@ class PhotoParams:
     seed: int = 0
     sample_offset: int = 0
     clip: bool = True
+    noise_clip: Sequence[bool] = (False, False, False, False)  # RandomGaussianNoiseWithClipping per stage
 
 
 @dataclass
@@ -210,7 +211,10 @@ def _plan_buffer(device, B: int, ow: int, oh: int):
     return buf, stride
 
 
-FIRST_WAVE_SAMPLES = 148  # sample clusters (2 CTAs) next to the canvas workers in the first wave of a 148-SM part
+FIRST_WAVE_SAMPLES = int(os.environ.get('B200AUG_FIRST_WAVE', '148'))  # sample clusters (2 CTAs) next to the canvas workers in the first wave of a 148-SM part
+
+
+ROTATED_FIRST_WAVE_COST = float(os.environ.get('B200AUG_ROT_COST', '1e9'))  # rotated samples at least this dear may start in the first wave
 
 
 def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams]) -> Optional[torch.Tensor]:
@@ -237,7 +241,7 @@ def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams])
     order = torch.argsort(cost, descending=True, stable=True)
     if rot is not None and bool(rot.any()):
         # the first wave: the dearest unrotated samples; everything else by cost behind them
-        r = rot[order]
+        r = rot[order] & (cost[order] < ROTATED_FIRST_WAVE_COST)
         head = order[~r][:FIRST_WAVE_SAMPLES]
         taken = torch.zeros(B, dtype=torch.bool)
         taken[head] = True
@@ -262,6 +266,8 @@ def marshal_photo(photo: PhotoParams, B: int, device) -> Tuple[Any, List[Any]]:
     p.apply, p.bits, p.gamma, p.contrast, p.brightness, p.noise_apply = (t.data_ptr() for t in (ap, bi, ga, co, br, na))
     for i, s in enumerate(photo.noise_std):
         p.noise_std[i] = float(s)
+    for i, c in enumerate(photo.noise_clip):
+        p.noise_clip[i] = int(bool(c))
     p.seed, p.sample_offset = int(photo.seed) & (2**64 - 1), int(photo.sample_offset)
     return p, [ap, bi, ga, co, br, na]
 
@@ -322,16 +328,31 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                 raise N.NativeError("semseg fields are not on the B200 path")
             continue
         code = _CAT_CODE.get(cat)
-        if code is None or not isinstance(v, torch.Tensor) or not v.is_floating_point() or k == "image_backtransform":
+        is_bt = k == "image_backtransform" and isinstance(v, torch.Tensor) and v.is_floating_point()
+        if is_bt:
+            # affinetrafo.py:137-147: every transform rewrites the back-transform as BT @ tr^-1, whatever its category;
+            # GeneralFocusRoi(insert_backtransform=True) starts it afresh instead (geometric.py:226-227)
+            if (flags & N.F_FOCUS) and insert_backtransform:
+                continue
+            if not (flags & (N.F_FOCUS | N.F_FLIPROT | N.F_NORMALIZE)):
+                out_data[k] = v
+                continue
+            code = N.CAT_BACKTRANSFORM
+        if code is None or not isinstance(v, torch.Tensor) or not v.is_floating_point():
             out_data[k] = v
             continue
         _require_cuda(v, k)
         t = v if batched else v[None]
         t = t.to(torch.float32).contiguous()
-        if t.shape[-1] not in _CAT_DIMS[code]:
-            raise ValueError(f"field {k!r} of category {cat.value!r} has last dim {t.shape[-1]}")
-        dim = t.shape[-1]
-        count = int(np.prod(t.shape[1:-1])) if t.dim() > 2 else 1
+        if is_bt:
+            if tuple(t.shape[1:]) != (2, 3):
+                raise ValueError(f"image_backtransform must be [..., 2, 3], got {tuple(v.shape)}")
+            dim, count = 6, 1
+        else:
+            if t.shape[-1] not in _CAT_DIMS[code]:
+                raise ValueError(f"field {k!r} of category {cat.value!r} has last dim {t.shape[-1]}")
+            dim = t.shape[-1]
+            count = int(np.prod(t.shape[1:-1])) if t.dim() > 2 else 1
         if nf >= N.MAX_FIELDS:
             raise N.NativeError(f"more than {N.MAX_FIELDS} label fields")
         o = torch.empty_like(t)
@@ -425,6 +446,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
         if insert_backtransform:
             bt = torch.empty((B, 2, 3), dtype=f32, device=device)
             args.backtransform_out = bt.data_ptr()
+            args.flags = flags | N.F_INSERT_BACKTRANSFORM
     if want_status:
         status = torch.empty((B,), dtype=torch.int32, device=device)
         args.status_out = status.data_ptr()
@@ -467,11 +489,13 @@ def apply_affine2d_fields(tr: torch.Tensor, fields: List[Tuple[FieldCategory, to
     arr = (N.Field * len(fields))()
     outs, keep = [], []
     for i, (cat, t) in enumerate(fields):
-        code = _CAT_CODE.get(as_category(cat), N.CAT_GENERAL)
         t = t.to(torch.float32).contiguous()
         o = torch.empty_like(t)
-        arr[i].category, arr[i].dim = code, t.shape[-1]
-        arr[i].count = int(np.prod(t.shape[1:-1])) if t.dim() > 2 else 1
+        if cat == "image_backtransform":  # (a key, not a category: BT @ tr^-1, affinetrafo.py:137-147)
+            arr[i].category, arr[i].dim, arr[i].count = N.CAT_BACKTRANSFORM, 6, 1
+        else:
+            arr[i].category, arr[i].dim = _CAT_CODE.get(as_category(cat), N.CAT_GENERAL), t.shape[-1]
+            arr[i].count = int(np.prod(t.shape[1:-1])) if t.dim() > 2 else 1
         arr[i].inp, arr[i].out = t.data_ptr(), o.data_ptr()
         outs.append(o)
         keep.append(t)

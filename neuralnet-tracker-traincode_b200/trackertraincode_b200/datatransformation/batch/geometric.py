@@ -96,18 +96,13 @@ class GeneralFocusRoi:
         geo = E.GeoParams(params.scales, params.angles, params.translations, E.host_cos_sin(params.angles))
         res = E.fused_forward(sample, flags=N.F_FOCUS, out_size=self.new_size, geo=geo, roi_variable=self.roi_variable,
                               beyond_border_shift=self._max_beyond_border_shift,
-                              insert_backtransform=self.insert_backtransform and "image_backtransform" not in sample,
-                              rowbuf_capacity=self.rowbuf_capacity)
-        had_bt = "image_backtransform" in sample
-        # like the reference, the passed sample (and its meta) is updated in place
+                              insert_backtransform=self.insert_backtransform, rowbuf_capacity=self.rowbuf_capacity)
+        # like the reference, the passed sample (and its meta) is updated in place.  An "image_backtransform" that is
+        # already there becomes BT @ tr^-1 (affinetrafo.py:137-147) -- unless insert_backtransform starts it afresh as tr^-1
+        # (geometric.py:226-227); both come out of the kernel.
         for k, v in res.batch.items():
             sample[k] = v
         if self.insert_backtransform:
-            if had_bt:  # affinetrafo.py:140-147: BT' = BT @ tr^-1
-                from ...neuralnets.affine2d import Affine2d
-
-                tr = res.tr if B != () else res.tr[0]
-                sample["image_backtransform"] = (Affine2d(sample["image_backtransform"]) @ Affine2d(tr).inv()).tensor()
             size = torch.tensor((W, H), dtype=torch.int32, device=sample.device)
             sample["image_original_size"] = size.expand(*B, 2).contiguous() if B != () else size
         sample.meta._imagesize = self.new_size

@@ -18,6 +18,7 @@ import torch
 from ... import _native as N
 from ...datasets.batch import Batch, FieldCategory, as_category
 from .. import _engine as E
+from .. import sharding
 
 
 def _range(v, default_hi=None) -> Tuple[float, float]:
@@ -94,6 +95,12 @@ class RandomGaussianNoise(_Op):
         self.std = float(std)
 
 
+class RandomGaussianNoiseWithClipping(RandomGaussianNoise):
+    """intensity.py:43-53: the noise op whose output is clipped to [0, 1] (on the samples it was applied to)."""
+
+    clip_output = True
+
+
 class OnlyClip(_Op):
     """intensity.py:56-64: clip(0, 1) -- the reference applies it with p=1."""
 
@@ -134,6 +141,7 @@ class KorniaImageDistortions:
         self.seed = seed
         self.bias = bias
         self.samples_seen = 0
+        self.calls = 0
 
     # -- sampling (host, torch global generator) ------------------------------------------------------------
     def draw(self, B: int) -> E.PhotoParams:
@@ -164,11 +172,16 @@ class KorniaImageDistortions:
                 brightness = uni(op.brightness)
         noise_apply = torch.zeros(B, N.NUM_NOISE, dtype=torch.bool)
         noise_std = [0.0] * N.NUM_NOISE
+        noise_clip = [False] * N.NUM_NOISE
         for s, op in enumerate(self.noise_ops):
             noise_apply[:, s] = torch.rand(B) < op.p
             noise_std[s] = op.std
+            noise_clip[s] = bool(getattr(op, "clip_output", False))
+        # noise stream keyed by a global sample id (sharding.py): ranks never share noise fields
+        rank, world = sharding.rank_world()
+        offset = sharding.global_sample_offset(self.calls, rank, world, B)
         return E.PhotoParams(order, apply, bits, gamma, contrast, brightness, noise_apply, tuple(noise_std), self.seed,
-                             self.samples_seen, self.clip)
+                             offset, self.clip, tuple(noise_clip))
 
     def __call__(self, batch: Batch, params: Optional[E.PhotoParams] = None) -> Batch:
         batch = copy(batch)
@@ -181,6 +194,7 @@ class KorniaImageDistortions:
             out = photometric_f32(x, p, bias=self.bias)
             batch[k] = out if batched else out[0]
             self.samples_seen += x.shape[0]
+            self.calls += 1
         return batch
 
 

@@ -40,7 +40,10 @@ def unnormalize_batch(sample: Batch) -> Batch:
         c = as_category(sample.meta.categories.get(k))
         if c == FieldCategory.image:
             out[k] = torch.clamp(v.mul(256.0), 0.0, 255.0).to(torch.uint8)
-        elif c in (FieldCategory.quat, FieldCategory.xys, FieldCategory.roi, FieldCategory.points) and k != "image_backtransform":
+        elif k == "image_backtransform":  # BT @ tr^-1 (affinetrafo.py:137-147)
+            names.append(k)
+            fields.append(("image_backtransform", v if batched else v[None]))
+        elif c in (FieldCategory.quat, FieldCategory.xys, FieldCategory.roi, FieldCategory.points):
             names.append(k)
             fields.append((c, v if batched else v[None]))
     if fields:

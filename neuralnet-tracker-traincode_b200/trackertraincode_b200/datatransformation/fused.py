@@ -9,6 +9,7 @@ return the *raw* sample (uint8 source frame + labels); frames of different sizes
 """
 from __future__ import annotations
 
+import collections
 from dataclasses import dataclass
 from typing import Optional
 
@@ -18,6 +19,7 @@ import torch
 from .. import _native as N
 from ..datasets.batch import Batch
 from . import _engine as E
+from . import sharding
 from .batch.geometric import MakeRoiRandomizationParameters, NoRoiRandomization, draw_flip_rot90
 
 # pipelines.py:510-527
@@ -86,6 +88,18 @@ class FusedPoseAugmentation:
         self.upload_row_bands = upload_row_bands and not zero_copy_frames
         self.uploaded_rows = 0   # rows copied host->device by the last call that used the row-band upload
         self._frames = {}        # device frame stacks the row bands land in, per (shape, stream)
+        self.steps = 0
+        # Host buffers (and everything else the asynchronous launch points at) stay referenced until the stream has passed
+        # the launch: the loader may drop its batch -- and its pin_memory thread reuse the pinned block -- while the copy
+        # or the kernel is still queued.
+        self._in_flight = collections.deque()
+
+    def _hold(self, stream, *objs):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._in_flight.append((ev, objs))
+        while self._in_flight and self._in_flight[0][0].query():
+            self._in_flight.popleft()
 
     def draw(self, B: int) -> AugmentationDraws:
         p = self.sampler((B,))
@@ -94,7 +108,11 @@ class FusedPoseAugmentation:
             do_flip, rot_dir = draw_flip_rot90(self.p_rot, (B,))
         else:
             do_flip, rot_dir = torch.zeros(B, dtype=torch.uint8), torch.zeros(B, dtype=torch.int8)
-        photo = draw_photo_params(B, self.seed, self.samples_seen) if self.enable_image_aug else None
+        # the noise stream is keyed by a GLOBAL sample id: (step * world + rank) * local batch (sharding.py), so ranks never
+        # share noise fields and a sample's noise does not depend on the world size
+        rank, world = sharding.rank_world()
+        offset = sharding.global_sample_offset(self.steps, rank, world, B)
+        photo = draw_photo_params(B, self.seed, offset) if self.enable_image_aug else None
         return AugmentationDraws(geo, do_flip, rot_dir, photo)
 
     def _to_device(self, batch: Batch) -> Batch:
@@ -194,12 +212,18 @@ class FusedPoseAugmentation:
             batch = batch.with_batchdim()
         (B,) = batch.meta.prefixshape
         d = params if params is not None else self._account_for_video(batch.meta, self.draw(B))
+        src_batch = batch
         if batch.device != self.device:
             batch = self._upload(batch, d)
         res = E.fused_forward(batch, flags=self.flags, out_size=self.inputsize, geo=d.geo, do_flip=d.do_flip,
                               rot_dir=d.rot_dir, photo=d.photo, rowbuf_capacity=self.rowbuf_capacity)
+        self._hold(torch.cuda.current_stream(self.device), src_batch, batch, res)
         self.samples_seen += B
+        self.steps += 1
         out = res.batch
+        for k, v in src_batch.items():  # normalization.py:26-30: bool fields become smoothed 0.1 / 0.9 float32 targets
+            if isinstance(v, torch.Tensor) and v.dtype == torch.bool:
+                out[k] = torch.where(out[k].to(torch.bool), 0.9, 0.1).to(torch.float32)
         meta = batch.meta.__class__(**{**batch.meta.__dict__})
         meta._imagesize = self.inputsize
         out.meta = meta

@@ -112,7 +112,7 @@ def gaussian_blur(x: np.ndarray, ksize=BLUR_KSIZE, sigma=BLUR_SIGMA) -> np.ndarr
 _M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _W0, _W1 = 0x9E3779B9, 0xBB67AE85
 _MASK = np.uint64(0xFFFFFFFF)
-NOISE_DOMAIN = 0x6E6F6973  # "nois": 4th counter word
+NOISE_DOMAIN = 0x6E6F6973  # "nois": 4th counter word, xor the high 32 bits of the sample id
 
 
 def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
@@ -144,7 +144,7 @@ def noise_field(seed: int, sample_id: int, stage: int, npix: int) -> np.ndarray:
     g, g+Q, g+2Q, g+3Q with Q = ceil(npix/4) -- the stride layout lets a warp store 32 consecutive floats."""
     q = (npix + 3) // 4
     g = np.arange(q, dtype=np.uint32)
-    x0, x1, x2, x3 = philox4x32_10(g, np.uint32(stage), np.uint32(sample_id & 0xFFFFFFFF), np.uint32(NOISE_DOMAIN),
+    x0, x1, x2, x3 = philox4x32_10(g, np.uint32(stage), np.uint32(sample_id & 0xFFFFFFFF), np.uint32(NOISE_DOMAIN ^ ((sample_id >> 32) & 0xFFFFFFFF)),
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     z0, z1 = _box_muller(x0, x1)
     z2, z3 = _box_muller(x2, x3)
@@ -169,11 +169,12 @@ class PhotoParams:
     seed: int = 0
     sample_offset: int = 0  # id of the batch's first sample in the noise stream
     clip: bool = True  # OnlyClip(p=1)
+    noise_clip: Sequence[bool] = (False,) * NUM_NOISE  # RandomGaussianNoiseWithClipping (intensity.py:43-53) per stage
 
     def slice(self, lo, hi):
         return PhotoParams(self.order, self.apply[lo:hi], self.bits[lo:hi], self.gamma[lo:hi], self.contrast[lo:hi],
                            self.brightness[lo:hi], self.noise_apply[lo:hi], self.noise_std, self.seed,
-                           self.sample_offset + lo, self.clip)
+                           self.sample_offset + lo, self.clip, self.noise_clip)
 
 
 def sample_photo_params(rng: np.random.Generator, B: int, seed: int = 0, sample_offset: int = 0,
@@ -226,6 +227,8 @@ def apply_stage2(x: np.ndarray, p: PhotoParams, b: int) -> np.ndarray:
         if p.noise_apply[b, s]:
             z = noise_field(p.seed, p.sample_offset + b, s, h * w).reshape(h, w)
             x = (x + F32(p.noise_std[s]) * z).astype(F32)
+            if p.noise_clip[s]:  # the clipping variant clamps the samples it was applied to (intensity.py:52)
+                x = np.clip(x, 0, 1).astype(F32)
     if p.clip:
         x = np.clip(x, 0, 1).astype(F32)
     return x
