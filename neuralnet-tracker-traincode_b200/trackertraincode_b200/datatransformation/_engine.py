@@ -70,12 +70,18 @@ class PreparedCall:
     `launch()` enqueues it on the current stream and can be repeated (same inputs -> same outputs), which is what a
     steady-state loop or a CUDA-graph capture wants."""
 
-    def __init__(self, args, device, result: FusedResult, keep):
+    def __init__(self, args, device, result: FusedResult, keep, bound_stream: Optional[int] = None):
         self.args, self.device, self.result, self._keep = args, device, result, keep
+        # a call that uses the per-(device, stream) scratch caches may only run on the stream it was prepared on: another
+        # stream's launches would share its canvases and plan records (private_scratch=True lifts the restriction)
+        self.bound_stream = bound_stream
 
     def launch(self, stream: Optional[int] = None, phase: int = N.PHASE_ALL) -> FusedResult:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.bound_stream is not None and stream != self.bound_stream:
+            raise N.NativeError("this call shares scratch buffers with other calls prepared on its stream; prepare it with "
+                                "private_scratch=True to launch it on a different stream")
         self.args.phase = phase
         N.check(N.lib.b200aug_fused_forward(C.byref(self.args), C.c_void_p(stream)), "b200aug_fused_forward")
         return self.result
@@ -426,7 +432,11 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
             keep.append(od)
             args.order = od.data_ptr()
     if (flags & N.F_FOCUS) and image_keys and use_workspace:
-        ws, stride = _workspace(device, B)
+        if private_scratch:
+            stride = int(N.lib.b200aug_workspace_stride(WORKSPACE_SIDE))
+            ws = torch.empty(B * stride, dtype=torch.uint8, device=device)
+        else:
+            ws, stride = _workspace(device, B)
         args.workspace, args.workspace_stride = ws.data_ptr(), stride
         keep.append(ws)
     if image_keys and preplan:
@@ -469,7 +479,44 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     ordered.update((k, v) for k, v in out_data.items() if k not in ordered)
     res = FusedResult(Batch(new_meta, ordered), view_roi, tr, status, trace)
     res._keep = keep  # inputs must outlive the asynchronous launch
-    return PreparedCall(args, device, res, keep)
+    shared = image_keys and not private_scratch and (preplan or ((flags & N.F_FOCUS) and use_workspace))
+    return PreparedCall(args, device, res, keep, torch.cuda.current_stream(device).cuda_stream if shared else None)
+
+
+class StatusWatch:
+    """Deferred check of the per-sample status arrays (B200AugFusedArgs.status_out): a degenerate roi (empty view box)
+    yields a zero-filled crop where the reference's cv2.resize raises.  The transforms copy the status of every call to
+    pinned host memory behind the launch and look at the copies whose event has passed at the next call -- no
+    synchronisation, the error surfaces one or two steps late; `flush()` (end of an epoch, tests) waits for all of them."""
+
+    def __init__(self):
+        self._pending = []
+
+    def watch(self, status: torch.Tensor, what: str):
+        host = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(status.device))
+        self._pending.append((ev, host, what))
+        self.poll()
+
+    def poll(self, wait: bool = False):
+        keep = []
+        for ev, host, what in self._pending:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                keep.append((ev, host, what))
+                continue
+            s = host.numpy()
+            bad = np.nonzero(s)[0]
+            if bad.size:
+                self._pending = []
+                raise N.NativeError(f"{what}: " + "; ".join(f"sample {i}: {STATUS_TEXT.get(int(s[i]), s[i])}" for i in bad[:8]))
+        self._pending = keep
+
+    def flush(self):
+        self.poll(wait=True)
 
 
 def raise_on_status(status: torch.Tensor):

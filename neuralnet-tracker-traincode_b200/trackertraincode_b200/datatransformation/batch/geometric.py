@@ -74,6 +74,7 @@ class GeneralFocusRoi:
         self._max_beyond_border_shift = 0.3
         self.make_randomization_parameters = make_randomization_parameters
         self.rowbuf_capacity = 0
+        self.status = E.StatusWatch()  # empty view boxes surface as NativeError (deferred; status.flush() waits)
 
     @staticmethod
     def _maybe_account_for_video(meta: Metadata, params: RoiFocusRandomizationParameters):
@@ -96,7 +97,9 @@ class GeneralFocusRoi:
         geo = E.GeoParams(params.scales, params.angles, params.translations, E.host_cos_sin(params.angles))
         res = E.fused_forward(sample, flags=N.F_FOCUS, out_size=self.new_size, geo=geo, roi_variable=self.roi_variable,
                               beyond_border_shift=self._max_beyond_border_shift,
-                              insert_backtransform=self.insert_backtransform, rowbuf_capacity=self.rowbuf_capacity)
+                              insert_backtransform=self.insert_backtransform, rowbuf_capacity=self.rowbuf_capacity,
+                              want_status=True)
+        self.status.watch(res.status, "GeneralFocusRoi")
         # like the reference, the passed sample (and its meta) is updated in place.  An "image_backtransform" that is
         # already there becomes BT @ tr^-1 (affinetrafo.py:137-147) -- unless insert_backtransform starts it afresh as tr^-1
         # (geometric.py:226-227); both come out of the kernel.

@@ -93,6 +93,7 @@ class FusedPoseAugmentation:
         # the launch: the loader may drop its batch -- and its pin_memory thread reuse the pinned block -- while the copy
         # or the kernel is still queued.
         self._in_flight = collections.deque()
+        self.status = E.StatusWatch()  # degenerate rois surface as NativeError one or two calls late (status.flush() waits)
 
     def _hold(self, stream, *objs):
         ev = torch.cuda.Event()
@@ -216,7 +217,8 @@ class FusedPoseAugmentation:
         if batch.device != self.device:
             batch = self._upload(batch, d)
         res = E.fused_forward(batch, flags=self.flags, out_size=self.inputsize, geo=d.geo, do_flip=d.do_flip,
-                              rot_dir=d.rot_dir, photo=d.photo, rowbuf_capacity=self.rowbuf_capacity)
+                              rot_dir=d.rot_dir, photo=d.photo, rowbuf_capacity=self.rowbuf_capacity, want_status=True)
+        self.status.watch(res.status, "FusedPoseAugmentation")
         self._hold(torch.cuda.current_stream(self.device), src_batch, batch, res)
         self.samples_seen += B
         self.steps += 1

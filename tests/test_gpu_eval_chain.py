@@ -232,3 +232,40 @@ def test_noise_with_clipping_vs_oracle():
     assert got[0].min() >= 0.0 and got[0].max() <= 1.0          # clipped stage applied
     assert got[1].min() < 0.0 and got[1].max() > 1.0            # only the plain stage: no clamp
     assert np.array_equal(got[3], x[3])                          # untouched sample passes through
+
+
+def test_degenerate_roi_raises_deferred():
+    """An empty view box zero-fills the crop; the mirror transforms report it (NativeError) at the next call / flush instead
+    of training on it silently (the reference's cv2.resize raises on the spot)."""
+    import trackertraincode_b200.datatransformation as dtr
+    from trackertraincode_b200 import _native as N
+
+    cs = [cases.make_case(i) for i in (0, 1, 5)]
+    cs[1]["roi"] = np.float32([80, 80, 80, 80])
+    focus = dtr.batch.FocusRoi(S, 1.1)
+    with pytest.raises(N.NativeError, match="sample 1: empty view box"):
+        focus(_frames(cs))    # (raises here already when the launch has finished by the time its status is looked at)
+        focus.status.flush()
+    ok = dtr.batch.FocusRoi(S, 1.1)
+    ok(_frames([cases.make_case(0)]))
+    ok.status.flush()
+
+
+def test_prepared_call_is_bound_to_its_stream_unless_private():
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datatransformation import _engine as E
+
+    cs = [cases.make_case(i) for i in (0, 1)]
+    geo = E.GeoParams(torch.tensor([1.1, 1.2]), torch.tensor([0.3, 0.0]), torch.zeros(2, 2))
+    shared = E.prepare_fused(_frames(cs), flags=N.F_FOCUS, out_size=S, geo=geo)
+    private = E.prepare_fused(_frames(cs), flags=N.F_FOCUS, out_size=S, geo=geo, private_scratch=True)
+    other = torch.cuda.Stream()
+    with pytest.raises(N.NativeError, match="private_scratch"):
+        shared.launch(other.cuda_stream)
+    a = shared.launch().batch["image"]
+    other.wait_stream(torch.cuda.current_stream())
+    private.launch_plan(other.cuda_stream)      # the two phases on a second stream, as a pipelined loop runs them
+    private.launch_main(other.cuda_stream)
+    other.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(a, private.result.batch["image"])
