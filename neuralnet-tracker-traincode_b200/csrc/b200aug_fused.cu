@@ -89,7 +89,8 @@ struct Plan {
 constexpr size_t WORKER_AREA = 2 * 512 * 8 + 1024 * 2 + 512 + 3 * 9392;  // = WK_AREA_BYTES (checked where that is defined)
 
 struct SmemLayout {
-  size_t off_tabs, off_tile, off_rowbuf, off_bars, off_prog, total;
+  size_t off_tabs, off_tile, off_rowbuf, off_bars, off_prog, off_wtab, total;
+  int wpad;  // columns of the dense tap-weight table (the band columns, padded to whole 128-column groups)
   int ntab;
 };
 
@@ -111,6 +112,13 @@ __host__ __device__ inline SmemLayout smem_layout(int ow, int oh, int cap) {
   o += 2 * sizeof(uint64_t);  // the cluster exchange barrier
   L.off_prog = o;
   o += (size_t)NWARPS * ROWPROG_CAP * sizeof(float2);
+  {
+    const int tail = ow % (32 * RMAX);
+    const int band = (tail != 0 && tail <= TAIL_COLS) ? ow - tail : ow;
+    L.wpad = (band + 32 * RMAX - 1) / (32 * RMAX) * (32 * RMAX);  // whole column groups: every lane of a group reads its entries
+  }
+  L.off_wtab = o;
+  o += (size_t)L.wpad * (KMAX + 1) * 4;  // dense tap weights [KMAX][wpad] + first-tap offsets [wpad]
   L.total = o;
   return L;
 }
@@ -877,6 +885,66 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
   return m;
 }
 
+// What every band of the CTA needs from cv2's resize tables, worked out ONCE per CTA by all threads (each warp used to
+// redo its share with lanes = rows / columns):
+//   prog[i], canvas row Rc0 + i of the CTA's output rows [rows_lo, rows_hi): (+-beta_a, beta_b) of the vertical pass --
+//     acc += beta_a * h; a minus sign on beta_a: the output row is complete -- store it, move on, restart the sum as
+//     beta_b * h (beta_b != 0 only when this canvas row is also the next output row's first tap);
+//   wtab[t * wpad + dx]: weight of tap t of band column dx, dense and zero padded (also zero for taps outside the frame:
+//     zero padding = weight +0, so only the in-frame part of a row is ever fetched);  xbt[dx]: first tap of the column
+//     relative to its 128-column group's fetched segment.
+// (The caller checked that the CTA's canvas rows fit the program.)
+__device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band, int rows_lo, int rows_hi, int cap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(ow, oh, cap);
+  const Plan& P = *reinterpret_cast<const Plan*>(smem);
+  const int* const tstart = reinterpret_cast<const int*>(smem + L.off_tabs);
+  const int* const tn = tstart + L.ntab;
+  const float* const ta = reinterpret_cast<const float*>(tn + L.ntab);
+  const float* const tb = ta + L.ntab;
+  const float* const tc = tb + L.ntab;
+  float2* const prog = reinterpret_cast<float2*>(smem + L.off_prog);
+  float* const wtab = reinterpret_cast<float*>(smem + L.off_wtab);
+  int* const xbt = reinterpret_cast<int*>(wtab + (size_t)KMAX * L.wpad);
+  const int tid = threadIdx.x;
+  auto row_end = [&](int d) { return tstart[ow + d] + (tn[ow + d] & 0xffff) - 1; };
+  const int Rc0 = tstart[ow + rows_lo], Rc1 = row_end(rows_hi - 1), n_rows = min(Rc1 - Rc0 + 1, NWARPS * ROWPROG_CAP);
+  const float inv_sy = (float)(1.0 / P.scale_y);
+  for (int i = tid; i < n_rows; i += NTHREADS) {
+    const int r = Rc0 + i;
+    // the lowest output row of this CTA that still uses canvas row r (estimate, then walk)
+    int d = min(max(rows_lo + (int)((float)i * inv_sy), rows_lo), rows_hi - 1);
+    while (d > rows_lo && row_end(d - 1) >= r) --d;
+    while (d < rows_hi - 1 && row_end(d) < r) ++d;
+    const int nf = tn[ow + d], yn = nf & 0xffff, k = r - tstart[ow + d];
+    float ba = 0.f, bb = 0.f;
+    bool emit = false;
+    if (k >= 0 && k < yn) {
+      ba = area_alpha(k, yn, nf & (1 << 30), nf & (1u << 31), ta[ow + d], tb[ow + d], tc[ow + d]);
+      emit = (k == yn - 1);
+      if (emit && d + 1 < rows_hi && tstart[ow + d + 1] == r) {
+        const int nf2 = tn[ow + d + 1];
+        bb = area_alpha(0, nf2 & 0xffff, nf2 & (1 << 30), nf2 & (1u << 31), ta[ow + d + 1], tb[ow + d + 1], tc[ow + d + 1]);
+      }
+    }
+    prog[i] = make_float2(emit ? -ba : ba, bb);
+  }
+  const int cfl = max(0, -P.x0), cfh = min(P.cw, P.sw - P.x0);
+  for (int dx = tid; dx < L.wpad; dx += NTHREADS) {
+    const bool valid = dx < ow_band;
+    const int g0 = dx & ~(32 * RMAX - 1);
+    const int dxc = valid ? dx : g0;
+    const int xnf = tn[dxc], xn = xnf & 0xffff, xs = tstart[dxc];
+    const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
+    const float xaf = ta[dxc], xam = tb[dxc], xal = tc[dxc];
+    xbt[dx] = xs - max(tstart[g0], cfl);
+    for (int t = 0; t < K; ++t) {
+      const int col = xs + t;
+      wtab[t * L.wpad + dx] = (valid && t < xn && col >= cfl && col < cfh) ? area_alpha(t, xn, xhf, xhl, xaf, xam, xal) : 0.f;
+    }
+  }
+}
+
 // cv2.resize INTER_AREA, general (non-integer) factor: each warp owns a band of output rows and streams the canvas
 // rows that feed it exactly once, in order.  Per canvas row: horizontal pass for the lane's columns (registers hold
 // the column taps), then the vertical accumulation in source-row order; a row shared by two output rows (fractional
@@ -921,36 +989,23 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   const int cfl = max(0, -x0), cfh = min(cw, sw - x0);
   const uint32_t rowbuf32 = smem_u32(rowbuf);
 
-  // ---- vertical-pass program of this warp's band: for canvas row R0 + i, prog[i] = (+-beta_a, beta_b):
-  //   acc += beta_a * h;  if beta_a carries a minus sign the output row is complete: store it, move to the next output
-  //   row and restart its sum as beta_b * h (beta_b != 0 only when this canvas row is also the next row's first tap).
-  // Built once (lanes = rows) from cv2's per-axis table, so the streaming loop below has no table logic left in it.
+  // ---- vertical-pass program (area_precompute): this band's canvas rows R0 .. R1 inside the CTA's program.  When the
+  // band's first canvas row is also the last tap of the output row above (which belongs to another warp), its entry
+  // (-beta_last, beta_first) must count as (beta_first, 0) here: `first_shared` patches the first entry on the fly.
   const int last = dy_end - 1;
   const int R0 = T.start[ow + dy_begin];
   const int R1 = T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
-  float2* const prog = reinterpret_cast<float2*>(smem + L.off_prog) + warp * ROWPROG_CAP;
-  for (int i = lane; i <= R1 - R0; i += 32) {
-    const int r = R0 + i;
-    int d = dy_begin;
-    while (d < last && T.start[ow + d] + (T.n[ow + d] & 0xffff) - 1 < r) ++d;
-    const int nf = T.n[ow + d], yn = nf & 0xffff, k = r - T.start[ow + d];
-    float ba = 0.f, bb = 0.f;
-    bool emit = false;
-    if (k >= 0 && k < yn) {
-      ba = area_alpha(k, yn, nf & (1 << 30), nf & (1u << 31), T.a[ow + d], T.b[ow + d], T.c[ow + d]);
-      emit = (k == yn - 1);
-      if (emit && d < last && T.start[ow + d + 1] == r) {
-        const int nf2 = T.n[ow + d + 1];
-        bb = area_alpha(0, nf2 & 0xffff, nf2 & (1 << 30), nf2 & (1u << 31), T.a[ow + d + 1], T.b[ow + d + 1], T.c[ow + d + 1]);
-      }
-    }
-    prog[i] = make_float2(emit ? -ba : ba, bb);
-  }
-  __syncwarp();
+  const float2* const prog = reinterpret_cast<const float2*>(smem + L.off_prog) + (R0 - T.start[ow + rows_lo]);
+  const bool band_first_shared = dy_begin > rows_lo && T.start[ow + dy_begin - 1] + (T.n[ow + dy_begin - 1] & 0xffff) - 1 >= R0;
+  const bool first_single = (T.n[ow + dy_begin] & 0xffff) == 1;  // (the shared row is the band's first output row's only tap)
+  const float* const wtab = reinterpret_cast<const float*>(smem + L.off_wtab);
+  const int* const xbt = reinterpret_cast<const int*>(wtab + (size_t)KMAX * L.wpad);
+  const int wpad = L.wpad;
 
   for (int g0 = 0; g0 < ow_band; g0 += 32 * RMAX) {
     const int gcols = min(32 * RMAX, ow_band - g0);
     const int glast = g0 + gcols - 1;
+    bool first_shared = band_first_shared;  // (every column group walks the band's rows from the top)
     const int seg_lo = max(T.start[g0], cfl);
     const int seg_hi = max(min(T.start[glast] + (T.n[glast] & 0xffff), cfh), seg_lo);
     const int seg_bytes = seg_hi - seg_lo;
@@ -1007,7 +1062,11 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     // vertical pass (see the program above); a fresh sum starts from +0, and 0 + x is exact
     const float2* pp = prog;
     auto vertical = [&](const float (&h)[RMAX]) {
-      const float2 pr = *pp++;
+      float2 pr = *pp++;
+      if (first_shared) {  // (only ever true for the band's first canvas row)
+        pr = make_float2(first_single ? -pr.y : pr.y, 0.f);
+        first_shared = false;
+      }
       const float ba = fabsf(pr.x);
 #pragma unroll
       for (int j = 0; j < RMAX; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(ba, h[j]));
@@ -1053,19 +1112,10 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     float w[RMAX][K];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
-      const int dx = g0 + 32 * j + lane;
-      const bool valid = dx <= glast;
-      const int dxc = valid ? dx : g0;
-      const int xnf = T.n[dxc], xn = xnf & 0xffff;
-      const bool xhf = xnf & (1 << 30), xhl = xnf & (1u << 31);
-      const float xaf = T.a[dxc], xam = T.b[dxc], xal = T.c[dxc];
-      const int xs = T.start[dxc];
-      xb[j] = xs - seg_lo;
+      const int dx = g0 + 32 * j + lane;  // (< wpad; columns past the band carry zero weights)
+      xb[j] = xbt[dx];
 #pragma unroll
-      for (int t = 0; t < K; ++t) {
-        const int col = xs + t;
-        w[j][t] = (valid && t < xn && col >= cfl && col < cfh) ? area_alpha(t, xn, xhf, xhl, xaf, xam, xal) : 0.f;
-      }
+      for (int t = 0; t < K; ++t) w[j][t] = wtab[t * wpad + dx];
     }
 
     int r = R0;
@@ -1836,11 +1886,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) && (P.src_mode != SRC_WARP) &&
               ow_band > 0;
   if (fast) {
-    // a warp's band of canvas rows must fit its vertical-pass program
-    // (the widest band of any CTA of the cluster: `fast` -- and with it `direct` -- must come out the same in all of them)
-    const int rows_per_warp = (((oh + cl - 1) >> cs) + 1 + NWARPS - 1) / NWARPS;
+    // the CTA's canvas rows must fit its vertical-pass program
+    // (the widest share of any CTA of the cluster: `fast` -- and with it `direct` -- must come out the same in all of them)
+    const int rows_per_cta = ((oh + cl - 1) >> cs) + 1;
     const int sy_ceil = (rs == RS_AREA_INT) ? P.iscale_y : (int)ceil(P.scale_y);
-    if ((rows_per_warp + 1) * sy_ceil + 2 > ROWPROG_CAP) fast = false;
+    if ((rows_per_cta + 1) * sy_ceil + 2 > NWARPS * ROWPROG_CAP) fast = false;
   }
   if (fast) {
     // every column group's canvas segment must fit the per-warp row buffer (only staged rows need it)
@@ -1858,6 +1908,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   if (cl > 1 && !direct) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   if (fast) {
     const int kx = P.kx;
+    area_precompute(kx <= 3 ? 3 : (kx == 4 ? 4 : 6), ow, oh, ow_band, rows_lo, rows_hi, cap);
+    __syncthreads();
     float* const gimg = direct ? a.image_f32_out + (size_t)b * npix : nullptr;
 #define B200AUG_BAND(KK) area_band<KK>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg)
     if (kx <= 3) B200AUG_BAND(3);
