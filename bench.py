@@ -186,6 +186,11 @@ def run_cpu_baseline(host, gp, pp, budget_s=12.0):
                        f"processes, {t:.1f} s wall; CPU: {cpu_model_name()}")
 
 
+def bench_config(world: int):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": world * BATCH}
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU implementation of the path (oracle port; the Python reference itself cannot travel to the
     GPU box) with every host core, one step = one 512-sample batch."""
@@ -210,7 +215,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "augmented_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": BATCH, "note": "runs on host cores of rank 0 only"},
+        "config": bench_config(args.gpus),
+        "details": {"note": "runs on the host cores of rank 0 only; one step = one 512-sample batch"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -260,6 +266,26 @@ class ClockSampler:
                 "power_w_max": float(max(power))}
 
 
+def pin_to_gpu_cores(gpu_index: int):
+    """Bind this rank (and the threads it spawns) to the host cores NVML reports as local to its GPU (same NUMA node / PCIe
+    root): eight ranks sampling parameters and driving 63 MB/step copies each otherwise wander over both sockets."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cores &= os.sched_getaffinity(0)
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:  # no NVML / not permitted: stay unpinned
+        pass
+    return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -274,12 +300,16 @@ def run_gpu_arm(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
-    # host data + the CPU baseline first (forking a pool after CUDA is initialised is asking for trouble)
-    hosts = [make_host_batch(1000 * rank + r) for r in range(RING)]
-    params = [draw_params(100 + 1000 * rank + r, BATCH, (rank * RING + r) * BATCH) for r in range(RING)]
+    # host data + the CPU baseline first (forking a pool after CUDA is initialised is asking for trouble).
+    # Weak scaling: every rank works on the SAME four batches and draws (per-GPU work is fixed as N grows; with per-rank
+    # seeds the max over ranks measured which rank had drawn the dearest samples -- SCALE_r01: 0.86 "efficiency" without
+    # any collective on the path); only the ids of the noise stream differ by rank.
+    hosts = [make_host_batch(r) for r in range(RING)]
+    params = [draw_params(100 + r, BATCH, (rank * RING + r) * BATCH) for r in range(RING)]
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu_baseline(hosts[0], *params[0])
+    affinity = pin_to_gpu_cores(local) if world > 1 and not args.no_pin else None
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -332,32 +362,50 @@ def run_gpu_arm(args):
     side = torch.cuda.Stream(dev)
     planned = [torch.cuda.Event() for _ in range(RING)]
     drained = [torch.cuda.Event() for _ in range(RING)]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    if pipelined:
-        side.wait_event(ev0)
-        calls[0].launch_plan(side.cuda_stream)
-        planned[0].record(side)
-        for s in range(args.steps):
-            r, nxt = s % RING, (s + 1) % RING
-            stream.wait_event(planned[r])
-            calls[r].launch_main(stream.cuda_stream)
-            drained[r].record(stream)
-            if s + 1 < args.steps:
-                if s + 1 >= RING:
-                    side.wait_event(drained[nxt])
-                calls[nxt].launch_plan(side.cuda_stream)
-                planned[nxt].record(side)
-    else:
-        for s in range(args.steps):
-            calls[s % RING].launch()
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+
+    def timed_window():
+        """EXACTLY args.steps steps between two events on the launching stream; returns milliseconds."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        if pipelined:
+            side.wait_event(ev0)
+            calls[0].launch_plan(side.cuda_stream)
+            planned[0].record(side)
+            for s in range(args.steps):
+                r, nxt = s % RING, (s + 1) % RING
+                stream.wait_event(planned[r])
+                calls[r].launch_main(stream.cuda_stream)
+                drained[r].record(stream)
+                if s + 1 < args.steps:
+                    if s + 1 >= RING:
+                        side.wait_event(drained[nxt])
+                    calls[nxt].launch_plan(side.cuda_stream)
+                    planned[nxt].record(side)
+        else:
+            for s in range(args.steps):
+                calls[s % RING].launch()
+        ev1.record(stream)
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    # A window of K steps is ~0.1 ms x K: at the driver's K = 20 that is 2 ms, where one stray interrupt moves the number
+    # by percent.  The K-step window is therefore timed `windows` times back to back (each with its own barriers and
+    # events) and the MEDIAN window is reported; min / max and the per-rank medians go into the line.
+    n_win = max(1, args.windows if args.windows > 0 else min(25, max(5, 2000 // max(args.steps, 1))))
+    wins = [timed_window() for _ in range(n_win)]
+    my_ms = float(np.median(wins))
+    per_rank = [my_ms]
     if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = my_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank = t.cpu().tolist()
+        # the job's time for a window is the slowest rank's: max over ranks, window by window, then the median
+        tw = torch.tensor(wins, device=dev, dtype=torch.float64)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wins = tw.cpu().tolist()
+    ms = float(np.median(wins))
     value = world * BATCH * args.steps / (ms * 1e-3)
 
     # ---- end-to-end through the public API from pinned host buffers
@@ -381,15 +429,17 @@ def run_gpu_arm(args):
         synchronised every step.  zero_copy: the frames stay in pinned host memory and the kernel reads them in place."""
         aug = FusedPoseAugmentation(OUT, rotation_aug_angle=30.0, roi_override="original", enable_image_aug=True, device=dev,
                                     zero_copy_frames=zero_copy, upload_row_bands=bands)
-        rows = []
+        rows, host_ms = [], []
 
         def e2e_step(s):
+            t_h = time.perf_counter()
             st = streams[s % 2] if pipelined else torch.cuda.current_stream(dev)
             with torch.cuda.stream(st):
                 out = aug(pinned[s % 2])
                 rows.append(aug.uploaded_rows)
                 for k in label_keys:
                     host_outs[s % 2][k].copy_(out[k], non_blocking=True)
+            host_ms.append((time.perf_counter() - t_h) * 1e3)  # host work of the step: sampling, marshalling, enqueueing
             if pipelined:
                 streams[(s - 1) % 2].synchronize()
             else:
@@ -401,20 +451,42 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         for s in range(e2e_steps):
             e2e_step(s)
+        torch.cuda.synchronize(dev)
+        mine = time.perf_counter() - t0
         barrier()
         e2e_s = time.perf_counter() - t0
+        per_rank_s = [mine]
         if world > 1:
+            t = torch.zeros(world + 1, device=dev, dtype=torch.float64)
+            t[rank] = mine
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank_s = t[:world].cpu().tolist()
             t = torch.tensor([e2e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        return world * BATCH * e2e_steps / e2e_s, float(np.mean(rows[-e2e_steps:]))
+        return dict(value=world * BATCH * e2e_steps / e2e_s, rows=float(np.mean(rows[-e2e_steps:])), per_rank_s=per_rank_s,
+                    host_ms=float(np.median(host_ms[-e2e_steps:])))
 
-    e2e_sync, _ = measure_e2e(False, False)
-    e2e_zero_copy, _ = measure_e2e(True, False)
-    e2e_full, _ = measure_e2e(False, True)
-    e2e_value, band_rows = measure_e2e(False, True, bands=True)
+    e2e = measure_e2e(False, True, bands=True)
+    e2e_value, band_rows = e2e["value"], e2e["rows"]
     h2d = label_bytes + int(band_rows * SRC)
+    e2e_variants = {}
+    if world == 1 and not args.quick:  # the other ways of getting the frames across, for the record (single GPU only)
+        e2e_variants = {
+            "whole_frames": {"value": measure_e2e(False, True)["value"], "h2d_bytes_per_step": label_bytes + frame_bytes,
+                             "note": "same, whole frames copied (upload_row_bands=False)"},
+            "whole_frames_synchronised_every_step": {"value": measure_e2e(False, False)["value"]},
+            "zero_copy_frames": {"value": measure_e2e(True, False)["value"],
+                                 "h2d_bytes_per_step": label_bytes + int(alg_bytes - BATCH * (OUT * OUT * 4 + LABEL_BYTES)),
+                                 "note": "frames left in pinned host memory and read in place by the kernel (only the view boxes "
+                                         "cross PCIe), synchronised every step"}}
     clocks = sampler.stop() if sampler else None
+    host_ms_all = [e2e["host_ms"]]
+    if world > 1:
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = e2e["host_ms"]
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        host_ms_all = t.cpu().tolist()
 
     if rank == 0:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -425,22 +497,32 @@ def run_gpu_arm(args):
             pass
         kernel_s = ms * 1e-3 / args.steps  # one fused kernel per step, event-timed on the launching stream
         achieved = alg_bytes / kernel_s / 1e9
-        traffic = None
-        try:
+        traffic = inst = None
+        prof_src = None
+        try:  # constants from the committed ncu capture of this kernel (profiles/), NOT measured in this run
             with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                prof = json.load(f)
+            traffic, inst, prof_src = prof.get("dram_bytes_per_launch"), prof.get("warp_instructions_per_launch"), prof.get("source")
         except (OSError, ValueError):
             pass
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = 148 * 4 * sm_hz  # warp instructions per second the 148 x 4 schedulers can issue
         line = {
             "metric": "augmented_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": world * BATCH,
-                       "l2": f"inputs larger than L2: ring of {RING} distinct batches ({RING * BATCH * SRC * SRC / 1e6:.0f} MB of sources)",
-                       "parallelism": f"per-sample sharding over {world} GPU(s), no collective",
-                       "loop": ("plan phase of step s+1 on a second stream next to the main phase of step s" if pipelined
-                                else "plan and main phase back to back on one stream"),
-                       **({"EXPERIMENT_dropped": os.environ["B200AUG_BENCH_DROP"]} if os.environ.get("B200AUG_BENCH_DROP") else {})},
+            "config": bench_config(world),
+            "details": {"l2": f"inputs larger than L2: ring of {RING} distinct batches ({RING * BATCH * SRC * SRC / 1e6:.0f} MB of sources)",
+                        "parallelism": f"per-sample sharding over {world} GPU(s), no collective; every rank works on the same "
+                                       "four batches and draws (weak scaling: fixed work per GPU)",
+                        "loop": ("plan phase of step s+1 on a second stream next to the main phase of step s" if pipelined
+                                 else "plan and main phase back to back on one stream"),
+                        "timing": f"median of {len(wins)} windows of exactly {args.steps} steps (CUDA events on the launching stream, "
+                                  "max over ranks per window)",
+                        "window_ms": {"min": float(min(wins)), "median": ms, "max": float(max(wins))},
+                        "per_rank_ms_per_step": [m / args.steps for m in per_rank],
+                        "cpu_affinity_cores": affinity,
+                        **({"EXPERIMENT_dropped": os.environ["B200AUG_BENCH_DROP"]} if os.environ.get("B200AUG_BENCH_DROP") else {})},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
@@ -448,16 +530,20 @@ def run_gpu_arm(args):
                             "and of the frame rows the sampled view boxes touch, b200aug_upload_row_bands; one fused launch) -> labels "
                             "read back into pinned host memory; two streams alternate and the host waits for step s-1 after enqueuing "
                             "step s, as a prefetching loader does",
-                    "whole_frames": {"value": e2e_full, "h2d_bytes_per_step": label_bytes + frame_bytes,
-                                     "note": "same, whole frames copied (upload_row_bands=False)"},
-                    "whole_frames_synchronised_every_step": {"value": e2e_sync},
-                    "zero_copy_frames": {"value": e2e_zero_copy, "h2d_bytes_per_step": label_bytes + int(alg_bytes - BATCH * (OUT * OUT * 4 + LABEL_BYTES)),
-                                         "note": "frames left in pinned host memory and read in place by the kernel (only the view "
-                                                 "boxes cross PCIe), synchronised every step"}},
+                    "per_rank": {"samples_per_s": [BATCH * e2e_steps / t for t in e2e["per_rank_s"]],
+                                 "h2d_GBps": [h2d * e2e_steps / t / 1e9 for t in e2e["per_rank_s"]],
+                                 "host_ms_per_step": host_ms_all},
+                    **e2e_variants},
             "gpu_launches": 2 * args.steps,  # plan_kernel + fused_augment_kernel per step
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fused_augment_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_us": kernel_s * 1e6, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": (f"{prof_src} (ncu capture of the same kernel and workload, a constant -- "
+                                                                "not measured in this run)" if traffic else None),
+                         "kernel": "fused_augment_kernel (+ plan_kernel on the side stream)", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_us": kernel_s * 1e6, "peak_source": peak_src,
+                         # what actually bounds the kernel: warp instructions issued against what the schedulers can issue
+                         "issue": ({"warp_instructions_per_launch": inst, "peak_warp_inst_per_s": issue_peak,
+                                    "achieved_warp_inst_per_s": inst / kernel_s, "frac": inst / kernel_s / issue_peak,
+                                    "floor_us_at_full_issue": inst / issue_peak * 1e6, "source": prof_src} if inst else None)},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
@@ -474,6 +560,9 @@ def main():
     ap.add_argument("--rowbuf", type=int, default=0, help="row-buffer capacity per warp slot (bytes), 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spin-s", type=float, default=0.6, help="minimum seconds of untimed warm-up launches (clock settling)")
+    ap.add_argument("--windows", type=int, default=0, help="how many times the K-step window is timed (median reported); 0 = auto")
+    ap.add_argument("--no-pin", action="store_true", help="do not bind ranks to their GPU's host cores (N > 1)")
+    ap.add_argument("--quick", action="store_true", help="skip the extra single-GPU e2e variants")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -86,7 +86,7 @@ struct Plan {
   int cv_pad;
 };
 
-constexpr size_t WORKER_AREA = 2 * 512 * 8 + 1024 * 2 + 512 + 3 * 9392;  // = WK_AREA_BYTES (checked where that is defined)
+constexpr size_t WORKER_AREA = 2 * 512 * 8 + 1024 * 2 + 128 + 32 * 48 + 3 * 9136;  // = WK_AREA_BYTES (checked where that is defined)
 
 struct SmemLayout {
   size_t off_tabs, off_tile, off_rowbuf, off_bars, off_prog, off_wtab, total;
@@ -1402,7 +1402,7 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
   if (tid == 0) {
     // rotated samples: the canvas goes to this sample's workspace region (if it fits), the canvas workers fill it
     bool canvas = false;
-    if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.status == B200AUG_S_OK && P.cw <= DT_CAP) {
+    if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.status == B200AUG_S_OK && P.cw <= DT_CAP && P.ch <= DT_CAP) {
       const int spitch = canvas_pitch(P.cw);
       if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
         P.cv_ptr = a.workspace + (size_t)b * a.workspace_stride;
@@ -1460,13 +1460,14 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
 // per-row alignment fix-up in the gather; B is 96 or 112, whichever spreads one canvas row's taps over more banks.
 constexpr int WK_CHUNKS = 4;                 // work items per rotated sample
 constexpr int WK_NSTAGE = 3;                 // staged tiles in flight per worker
+constexpr int WK_MAX_ITEM_TILES = 32;        // tiles of one work item: a 512 x 512 canvas has 8 x 16 tiles, a quarter of them
 constexpr int WT2_W = 64, WT2_H = 32;        // canvas tile of one pipeline step
-constexpr int WT2_ROWS = 74;                 // tallest staged bounding box
+constexpr int WT2_ROWS = 72;                 // tallest staged bounding box (a 64 x 32 tile turned by 45 degrees: 71 rows)
 constexpr int WT2_NCH = 6;                   // 16-byte chunks staged per box row (box width + alignment shift <= 96)
 constexpr int WT2_B0 = 96, WT2_B1 = 112;     // candidate row strides (+ pitch mod 16)
 constexpr int WT2_STAGE = ((WT2_ROWS - 1) * (WT2_B1 + 15) + 15 + 16 * WT2_NCH + 15) & ~15;
 constexpr int WK_OFF_RTAB = DT_CAP * 8, WK_OFF_LIST = 2 * DT_CAP * 8, WK_OFF_SH = WK_OFF_LIST + WK_SLICE * 2,
-              WK_OFF_STAGE = WK_OFF_SH + 512, WK_AREA_BYTES = WK_OFF_STAGE + WK_NSTAGE * WT2_STAGE;
+              WK_OFF_STAGE = WK_OFF_SH + 128 + WK_MAX_ITEM_TILES * 48, WK_AREA_BYTES = WK_OFF_STAGE + WK_NSTAGE * WT2_STAGE;
 
 static_assert(WK_AREA_BYTES == (int)WORKER_AREA, "smem_layout reserves WORKER_AREA bytes for a canvas worker");
 
@@ -1474,6 +1475,7 @@ struct TileMeta {
   int x_lo, y_lo, tw, th, bx0, bx1, by0, c0, nrows, mode;  // mode 0 staged | 1 staged, columns outside the frame | 2 not staged
   int pad[2];
 };
+static_assert(sizeof(TileMeta) == 48, "WK_OFF_STAGE");
 
 // geometry of canvas tile (tx, ty): bounding box of its taps in the source, staging decision.  One thread.
 __device__ __forceinline__ void wk_tile_meta(const Plan& P, const int2* dtab, const int2* rtab, int tx, int ty, TileMeta* meta) {
@@ -1571,14 +1573,16 @@ __device__ __forceinline__ void wk_compute_tile(const Plan& P, const int2* dtab,
     dyk[h] = d.y - (m.by0 << 10);
     act[h] = xi < m.tw;
   }
-  const uint32_t ro32 = smem_u32(rtab + m.y_lo + warp);
+  const int2* const rorow = rtab + m.y_lo + warp;
   uint8_t* out = canvas + (size_t)(m.y_lo + warp) * spitch + m.x_lo + lane;
   const size_t out_step = (size_t)NWARPS * spitch;
-  const int n_it = (m.th - warp + NWARPS - 1) / NWARPS;  // rows warp, warp + 8, ...
-#pragma unroll 2
-  for (int it = 0; it < n_it; ++it) {
-    int rox, roy;
-    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(rox), "=r"(roy) : "r"(ro32 + (uint32_t)it * (NWARPS * 8)) : "memory");
+  const int n_it = (m.th - warp + NWARPS - 1) / NWARPS;  // rows warp, warp + 8, ...: at most WT2_H / NWARPS = 4 of them
+  static_assert(WT2_H == 4 * NWARPS, "the row loop below is unrolled four times");
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (it >= n_it) break;
+    const int2 ro = rorow[it * NWARPS];
+    const int rox = ro.x, roy = ro.y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t sx = (uint32_t)rox + (uint32_t)dxk[h];  // 1/1024 px, offset by K
@@ -1604,7 +1608,7 @@ __device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, u
   int2* const rtab = reinterpret_cast<int2*>(area + WK_OFF_RTAB);
   uint16_t* const list = reinterpret_cast<uint16_t*>(area + WK_OFF_LIST);
   int* const sh = reinterpret_cast<int*>(area + WK_OFF_SH);  // [0] n_list, [1] item, [2..9] warp counts, [10..17] bases
-  TileMeta* const meta = reinterpret_cast<TileMeta*>(area + WK_OFF_SH + 128);
+  TileMeta* const meta = reinterpret_cast<TileMeta*>(area + WK_OFF_SH + 128);  // [WK_MAX_ITEM_TILES], the current item's tiles
   uint8_t* const stage = area + WK_OFF_STAGE;
   const uint32_t stage32 = smem_u32(stage);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1678,46 +1682,39 @@ __device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, u
       __syncthreads();
       const int tiles_x = (cw + WT2_W - 1) / WT2_W, tiles_y = (ch + WT2_H - 1) / WT2_H, n_tiles = tiles_x * tiles_y;
       const int t_begin = (chunk * n_tiles) / WK_CHUNKS, t_end = ((chunk + 1) * n_tiles) / WK_CHUNKS;
-      // ---- the tile pipeline: the copies of tile t + WK_NSTAGE - 1 are issued before tile t is gathered; thread 0 works
-      // out the geometry of a tile (meta ring of WK_NSTAGE + 1) one step before its copies are issued
-      int mtx = 0, mty = 0, mt = t_begin;  // thread 0: the next tile to describe
-      if (tid == 0) {
-        mty = t_begin / tiles_x;
-        mtx = t_begin - mty * tiles_x;
+      // ---- the tile pipeline: the copies of tile t + WK_NSTAGE - 1 are issued before tile t is gathered.  The geometry of
+      // all the item's tiles (at most WK_MAX_ITEM_TILES) is worked out first, one thread per tile.
+      if (tid < t_end - t_begin) {
+        const int t = t_begin + tid, ty = t / tiles_x;
+        wk_tile_meta(P, dtab, rtab, t - ty * tiles_x, ty, meta + tid);
       }
-      auto describe = [&]() {
-        if (tid == 0 && mt < t_end) {
-          wk_tile_meta(P, dtab, rtab, mtx, mty, meta + (mt - t_begin) % (WK_NSTAGE + 1));
-          ++mt;
-          if (++mtx == tiles_x) { mtx = 0; ++mty; }
-        }
-      };
-      for (int s2 = 0; s2 < WK_NSTAGE; ++s2) describe();
       __syncthreads();
 #pragma unroll 1
       for (int s2 = 0; s2 < WK_NSTAGE - 1; ++s2) {
         if (t_begin + s2 < t_end) wk_issue_tile(P, meta[s2], bstride, stage32 + s2 * WT2_STAGE, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
+      int sl = 0, sn = WK_NSTAGE - 1;  // stage of tile t / of tile t + WK_NSTAGE - 1
 #pragma unroll 1
       for (int t = t_begin; t < t_end; ++t) {
-        const int i = t - t_begin, sl = i % WK_NSTAGE, ia = i + WK_NSTAGE - 1, sn = ia % WK_NSTAGE;
+        const int i = t - t_begin;
         const long long c0 = tr ? clock64() : 0;
-        if (t + WK_NSTAGE - 1 < t_end) wk_issue_tile(P, meta[ia % (WK_NSTAGE + 1)], bstride, stage32 + sn * WT2_STAGE, tid);
+        if (t + WK_NSTAGE - 1 < t_end) wk_issue_tile(P, meta[i + WK_NSTAGE - 1], bstride, stage32 + sn * WT2_STAGE, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
         static_assert(WK_NSTAGE == 3, "wait_group immediate");
         const long long c1 = tr ? clock64() : 0;
         asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's copies of tile t have landed ...
         __syncthreads();                                      // ... and everybody else's
         const long long c2 = tr ? clock64() : 0;
-        wk_compute_tile(P, dtab, rtab, meta + i % (WK_NSTAGE + 1), bstride, stage + sl * WT2_STAGE, warp, lane, tid);
+        wk_compute_tile(P, dtab, rtab, meta + i, bstride, stage + sl * WT2_STAGE, warp, lane, tid);
         const long long c3 = tr ? clock64() : 0;
-        describe();       // tile t + WK_NSTAGE (its slot held tile t - 1, which nobody reads any more)
-        __syncthreads();  // the stage is free again, the new description visible
-        if (tr && tid == 0) {  // (profiling: cycles in issue / wait / gather / describe + barrier, tiles)
+        __syncthreads();  // the stage is free again
+        if (tr && tid == 0) {  // (profiling: cycles in issue / wait / gather / barrier, tiles)
           const long long c4 = clock64();
           tr[8] += (uint64_t)(c1 - c0); tr[9] += (uint64_t)(c2 - c1); tr[10] += (uint64_t)(c3 - c2); tr[11] += (uint64_t)(c4 - c3); tr[12] += 1;
         }
+        sl = (sl + 1 == WK_NSTAGE) ? 0 : sl + 1;
+        sn = (sn + 1 == WK_NSTAGE) ? 0 : sn + 1;
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();   // every thread's canvas pixels are written ...
