@@ -1458,9 +1458,12 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
 // Staged layout (as warp_canvas_to_scratch): box row r lands at offset B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift
 // of row 0, pm = pitch mod 16, so that source pixel (iy, ix) sits at c0 + (iy - by0)(B + pm) + (ix - bx0): linear, no
 // per-row alignment fix-up in the gather; B is 96 or 112, whichever spreads one canvas row's taps over more banks.
-constexpr int WK_CHUNKS = 4;                 // work items per rotated sample
+#ifndef B200AUG_WK_CHUNKS
+#define B200AUG_WK_CHUNKS 4
+#endif
+constexpr int WK_CHUNKS = B200AUG_WK_CHUNKS;  // work items per rotated sample
 constexpr int WK_NSTAGE = 3;                 // staged tiles in flight per worker
-constexpr int WK_MAX_ITEM_TILES = 32;        // tiles of one work item: a 512 x 512 canvas has 8 x 16 tiles, a quarter of them
+constexpr int WK_MAX_ITEM_TILES = 32;        // tiles of one work item whose geometry is worked out in one go
 constexpr int WT2_W = 64, WT2_H = 32;        // canvas tile of one pipeline step
 constexpr int WT2_ROWS = 72;                 // tallest staged bounding box (a 64 x 32 tile turned by 45 degrees: 71 rows)
 constexpr int WT2_NCH = 6;                   // 16-byte chunks staged per box row (box width + alignment shift <= 96)
@@ -1637,10 +1640,12 @@ __device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, u
     const int n_items = sh[0] * WK_CHUNKS;
     // ---- work stealing over (sample, chunk)
     for (;;) {
+      const long long i0 = tr ? clock64() : 0;
       if (tid == 0) sh[1] = (int)atomicAdd(&tail.counters[slice], 1u);
       __syncthreads();
       const int item = sh[1];
       if (item >= n_items) break;
+      const long long i1 = tr ? clock64() : 0;
       const int pos = base + list[item / WK_CHUNKS], chunk = item % WK_CHUNKS;
       const int b = a.order ? a.order[pos] : pos;
       {
@@ -1681,9 +1686,14 @@ __device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, u
       }
       __syncthreads();
       const int tiles_x = (cw + WT2_W - 1) / WT2_W, tiles_y = (ch + WT2_H - 1) / WT2_H, n_tiles = tiles_x * tiles_y;
-      const int t_begin = (chunk * n_tiles) / WK_CHUNKS, t_end = ((chunk + 1) * n_tiles) / WK_CHUNKS;
+      const int it_begin = (chunk * n_tiles) / WK_CHUNKS, it_end = ((chunk + 1) * n_tiles) / WK_CHUNKS;
+      long long i2 = 0;
       // ---- the tile pipeline: the copies of tile t + WK_NSTAGE - 1 are issued before tile t is gathered.  The geometry of
-      // all the item's tiles (at most WK_MAX_ITEM_TILES) is worked out first, one thread per tile.
+      // the tiles (WK_MAX_ITEM_TILES at a time: all of the item's unless the canvas is very large) is worked out first, one
+      // thread per tile.
+#pragma unroll 1
+      for (int t_begin = it_begin; t_begin < it_end; t_begin += WK_MAX_ITEM_TILES) {
+      const int t_end = min(t_begin + WK_MAX_ITEM_TILES, it_end);
       if (tid < t_end - t_begin) {
         const int t = t_begin + tid, ty = t / tiles_x;
         wk_tile_meta(P, dtab, rtab, t - ty * tiles_x, ty, meta + tid);
@@ -1694,6 +1704,7 @@ __device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, u
         if (t_begin + s2 < t_end) wk_issue_tile(P, meta[s2], bstride, stage32 + s2 * WT2_STAGE, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
+      if (t_begin == it_begin) i2 = tr ? clock64() : 0;
       int sl = 0, sn = WK_NSTAGE - 1;  // stage of tile t / of tile t + WK_NSTAGE - 1
 #pragma unroll 1
       for (int t = t_begin; t < t_end; ++t) {
@@ -1716,11 +1727,18 @@ __device__ __noinline__ void canvas_worker(const B200AugFusedArgs& a, Plan& P, u
         sl = (sl + 1 == WK_NSTAGE) ? 0 : sl + 1;
         sn = (sn + 1 == WK_NSTAGE) ? 0 : sn + 1;
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // (only empty groups are left)
+      }
+      const long long i3 = tr ? clock64() : 0;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();   // every thread's canvas pixels are written ...
       if (tid == 0) {
         __threadfence();  // ... and visible device-wide (cumulative over the barrier) before the completion counter moves
         atomicAdd(&tail.done[b], 1u);
+        if (tr) {  // (profiling: cycles for the work-item fetch / plan + tables + tile geometry + first copies / tail, items)
+          const long long i4 = clock64();
+          tr[13] += (uint64_t)(i1 - i0); tr[14] += (uint64_t)(i2 - i1); tr[15] += (uint64_t)(i4 - i3); tr[7] += 1;
+        }
       }
       ++n_done;
     }

@@ -47,6 +47,10 @@ if len(tw):
     nt = max(int(tw[:, 12].sum()), 1)
     print("canvas workers, cycles per tile (thread 0): issue %.0f wait %.0f gather %.0f describe+barrier %.0f; tiles %d; total CTA-us %.0f" % (
         tw[:, 8].sum() / nt, tw[:, 9].sum() / nt, tw[:, 10].sum() / nt, tw[:, 11].sum() / nt, nt, (tw[:, 4] - tw[:, 0]).sum() / 1e3))
+if len(tw):
+    ni = max(int(tw[:, 7].sum()), 1)
+    print("canvas workers, cycles per item (thread 0): fetch %.0f setup %.0f tail %.0f; items %d" % (
+        tw[:, 13].sum() / ni, tw[:, 14].sum() / ni, tw[:, 15].sum() / ni, ni))
 start, plan, tabs, res, end, smid = (t[:, i] - (t0 if i < 5 else 0) for i in range(6))
 print(f"kernel span {(end.max()) / 1e3:.1f} us; CTA duration us: mean {np.mean(end - start) / 1e3:.1f} median {np.median(end - start) / 1e3:.1f} "
       f"p95 {np.percentile(end - start, 95) / 1e3:.1f} max {(end - start).max() / 1e3:.1f}")
