@@ -1162,19 +1162,26 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
 
 // ------------------------------------------------------------------------------------------------ photometric helpers
 
+constexpr float R255 = 0x1.010102p-8f;  // float32(1 / 255)
+
 // pointwise stage-1 ops [from, to) of this sample's op list applied to x (oracle/photometric.py)
 __device__ __noinline__ float apply_point_ops(const Plan& P, float x, int from, int to, const float* eq_lut) {
   for (int k = from; k < to; ++k) {
     switch (P.ops[k]) {
       case B200AUG_OP_EQUALIZE: {
+        // kornia's `result / 255.0` runs on the GPU in the reference's pipeline, where torch divides a tensor by a host
+        // scalar as a multiplication with the rounded reciprocal (oracle/photometric.py: R255)
         float im = __fmul_rn(x, 255.f);
-        if (P.eq_step0) x = __fdiv_rn(im, 255.f);
-        else x = __fdiv_rn(eq_lut[min(max((int)im, 0), 255)], 255.f);
+        if (P.eq_step0) x = __fmul_rn(im, R255);
+        else x = __fmul_rn(eq_lut[min(max((int)im, 0), 255)], R255);
       } break;
       case B200AUG_OP_POSTERIZE: {
-        int q = (int)__fmul_rn(x, 255.f) & 255;
-        int sh = 8 - P.bits;
-        x = __fdiv_rn((float)((q >> sh) << sh), 255.f);
+        // kornia.enhance.posterize, literally: right shift = uint8(x * 255) / 2^s / 255, left shift = uint8(that * 255) * 2^s / 255
+        const int q = (int)__fmul_rn(x, 255.f) & 255;
+        const int sh = 8 - P.bits;
+        const float right = __fmul_rn(__fmul_rn((float)q, __int_as_float((127 - sh) << 23)), R255);
+        const int l = ((int)__fmul_rn(right, 255.f) & 255) << sh;
+        x = __fmul_rn((float)(l & 255), R255);
       } break;
       case B200AUG_OP_GAMMA: {
         const float pw = powf(x, P.gamma);

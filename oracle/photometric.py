@@ -34,6 +34,11 @@ BRIGHTNESS_RANGE = (0.7, 1.5)
 BLUR_KSIZE, BLUR_SIGMA = 5, 1.5
 
 
+# kornia's `x / 255.0`: the reference runs these ops on CUDA tensors (pipelines.py:508-527), where torch evaluates a tensor
+# divided by a host scalar as a multiplication with the float32 reciprocal -- one ulp away from the true quotient now and
+# then.  tests/test_gpu_photometric_torch.py checks the CUDA kernels bit for bit against the torch primitives on the GPU.
+R255 = F32(1.0) / F32(255.0)
+
 # ----------------------------------------------------------------------------- point ops
 
 
@@ -49,17 +54,20 @@ def equalize(x: np.ndarray) -> np.ndarray:
     nz = h[h != 0]
     step = (int(nz.sum()) - int(nz[-1])) // 255 if nz.size else 0
     if step == 0:
-        return (im / F32(255.0)).astype(F32)
+        return (im * R255).astype(F32)
     lut = (np.cumsum(h) + step // 2) // step
     lut = np.clip(np.concatenate([[0], lut[:-1]]), 0, 255).astype(F32)
-    return (lut[np.clip(im.astype(np.int64), 0, 255)] / F32(255.0)).astype(F32)
+    return (lut[np.clip(im.astype(np.int64), 0, 255)] * R255).astype(F32)
 
 
 def posterize(x: np.ndarray, bits: int) -> np.ndarray:
-    """kornia.enhance.posterize: keep the top `bits` bits of uint8(x*255)."""
-    q = (np.asarray(x, F32) * F32(255.0)).astype(np.uint8)
+    """kornia.enhance.posterize, literally: _left_shift(_right_shift(x, s), s) with s = 8 - bits, where
+    _right_shift = uint8(x * 255) / 2**s / 255 and _left_shift = uint8(x * 255) * 2**s / 255 (float32, `/ 255` as R255)."""
     shift = 8 - int(bits)
-    return (((q >> shift) << shift).astype(F32) / F32(255.0)).astype(F32)
+    q = (np.asarray(x, F32) * F32(255.0)).astype(np.uint8)
+    right = ((q.astype(F32) / F32(2**shift)) * R255).astype(F32)
+    left = ((right * F32(255.0)).astype(np.uint8).astype(np.int64) * (2**shift)) & 255
+    return (left.astype(F32) * R255).astype(F32)
 
 
 def gamma(x: np.ndarray, g: float) -> np.ndarray:

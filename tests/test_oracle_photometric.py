@@ -15,10 +15,12 @@ def test_posterize_hand_vector():
     x = np.array([[0, 15, 16, 200, 255]], F) / F(256)  # normalize_batch scale
     q = (x * F(255)).astype(np.uint8)                  # 0, 14, 15, 199, 254
     assert q.tolist() == [[0, 14, 15, 199, 254]]
+    # the grey levels are exact; the final `/ 255.0` follows torch's GPU semantics (multiplication by float32(1/255))
     got = P.posterize(x, 4)
-    assert np.array_equal(got, (np.array([[0, 0, 0, 192, 240]], F) / F(255)).astype(F))
+    assert np.array_equal(got, (np.array([[0, 0, 0, 192, 240]], F) * P.R255).astype(F))
+    assert np.allclose(got, np.array([[0, 0, 0, 192, 240]], F) / F(255), rtol=0, atol=6e-8)
     got6 = P.posterize(x, 6)
-    assert np.array_equal(got6, (np.array([[0, 12, 12, 196, 252]], F) / F(255)).astype(F))
+    assert np.array_equal(got6, (np.array([[0, 12, 12, 196, 252]], F) * P.R255).astype(F))
 
 
 def test_gamma_contrast_brightness_hand_vectors():
