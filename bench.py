@@ -557,6 +557,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="augment", choices=["augment", "train"],
+                    help="augment: the hot path alone (the contract line); train: configs[2]/[3], ResNet-18 training step with the "
+                         "augmentation on a side stream and DDP all-reduce (scripts/train_bench.py)")
     ap.add_argument("--rowbuf", type=int, default=0, help="row-buffer capacity per warp slot (bytes), 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spin-s", type=float, default=0.6, help="minimum seconds of untimed warm-up launches (clock settling)")
@@ -564,7 +567,15 @@ def main():
     ap.add_argument("--no-pin", action="store_true", help="do not bind ranks to their GPU's host cores (N > 1)")
     ap.add_argument("--quick", action="store_true", help="skip the extra single-GPU e2e variants")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "train":
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import train_bench
+
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        line = train_bench.run(256 if world > 1 else 128, max(args.steps, 10) if args.steps != 200 else 40, max(args.warmup, 5), False)
+        if line is not None:
+            print(json.dumps(line))
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

@@ -120,6 +120,60 @@ def _dev(t, device, dtype) -> torch.Tensor:
     return t.contiguous()
 
 
+class _HostPack:
+    """All the small host-side parameter arrays of one call travel as ONE pinned staging buffer and ONE host->device copy
+    (a dozen pageable `.to(device)` calls cost more host time than the kernel takes).  `add` returns a token; after
+    `upload()` `ptr(token)` is the device address of that array."""
+
+    _pools: Dict[Any, List[Any]] = {}  # device -> [(pinned buffer, event of its last upload)]
+
+    def __init__(self, device):
+        self.device = device
+        self.items: List[Tuple[int, torch.Tensor]] = []
+        self.total = 0
+        self.dev: Optional[torch.Tensor] = None
+
+    def add(self, t, dtype, shape):
+        t = torch.as_tensor(t)
+        if t.is_cuda:  # already on the device: used in place
+            t = t.to(dtype).reshape(shape).contiguous()
+            return ("dev", t)
+        t = t.to(dtype).reshape(shape).contiguous()
+        off = (self.total + 15) & ~15
+        self.total = off + t.numel() * t.element_size()
+        self.items.append((off, t))
+        return ("pack", off)
+
+    def upload(self, stream) -> List[Any]:
+        if not self.items:
+            return []
+        pool = self._pools.setdefault((self.device.type, self.device.index), [])
+        slot = None
+        for i, (buf, ev) in enumerate(pool):
+            if buf.numel() >= self.total and ev.query():
+                slot = i
+                break
+        if slot is None:
+            pool.append((torch.empty(max(self.total, 1 << 16), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()))
+            slot = len(pool) - 1
+        buf, ev = pool[slot]
+        for off, t in self.items:
+            n = t.numel() * t.element_size()
+            buf[off:off + n].copy_(t.reshape(-1).view(torch.uint8))
+        self.dev = torch.empty(self.total, dtype=torch.uint8, device=self.device)
+        self.dev.copy_(buf[:self.total], non_blocking=True)
+        ev.record(stream)
+        return [self.dev]
+
+    def ptr(self, token) -> int:
+        kind, v = token
+        return v.data_ptr() if kind == "dev" else self.dev.data_ptr() + v
+
+    @staticmethod
+    def keep(token) -> List[Any]:
+        return [token[1]] if token[0] == "dev" else []
+
+
 def host_cos_sin(angles: torch.Tensor) -> Optional[torch.Tensor]:
     """cos/sin evaluated exactly like the reference does on the host (Affine2d.trs, affine2d.py:46-47); None when the
     angles already live on the device (the kernel then uses the correctly rounded values)."""
@@ -227,54 +281,62 @@ def launch_order(B: int, geo: Optional[GeoParams], photo: Optional[PhotoParams])
     """Launch order of the fused kernel's clusters (B200AugFusedArgs.order): most expensive photometric chains first, but
     no rotated sample in the first wave -- their canvases come from the canvas workers, which start with the first wave
     and walk the rotated samples in this same order.  Only parameters that are still on the host are looked at -- this never
-    synchronises with the device; returns None when nothing distinguishes the samples."""
-    cost = torch.zeros(B)
+    synchronises with the device; returns None when nothing distinguishes the samples.  (numpy: a few small arrays.)"""
+    cost = np.zeros(B, np.float32)
     known = False
     if photo is not None and not torch.as_tensor(photo.apply).is_cuda:
         # relative to a plain crop (15 us per CTA in the r02 trace): blur +20 us, equalize +3, a noise stage +5
-        ap = torch.as_tensor(photo.apply).reshape(B, N.NUM_OPS).bool()
-        chosen = torch.zeros(N.NUM_OPS, dtype=torch.bool)
+        ap = torch.as_tensor(photo.apply).reshape(B, N.NUM_OPS).numpy().astype(bool)
+        chosen = np.zeros(N.NUM_OPS, bool)
         chosen[list(photo.order)] = True
-        cost += (ap[:, 5] & chosen[5]).float() * 1.3 + (ap[:, 0] & chosen[0]).float() * 0.2
-        cost += torch.as_tensor(photo.noise_apply).reshape(B, N.NUM_NOISE).float().sum(1) * 0.35
+        cost += (ap[:, 5] & chosen[5]) * np.float32(1.3) + (ap[:, 0] & chosen[0]) * np.float32(0.2)
+        cost += torch.as_tensor(photo.noise_apply).reshape(B, N.NUM_NOISE).numpy().astype(np.float32).sum(1) * np.float32(0.35)
         known = True
     rot = None
     if geo is not None and not geo.angles.is_cuda:
-        rot = geo.angles.reshape(B) != 0
+        rot = geo.angles.reshape(B).numpy() != 0
         known = known or bool(rot.any())
-    if not known or (float(cost.max()) == float(cost.min()) and (rot is None or not bool(rot.any()))):
+    if not known or (float(cost.max()) == float(cost.min()) and (rot is None or not rot.any())):
         return None
-    order = torch.argsort(cost, descending=True, stable=True)
-    if rot is not None and bool(rot.any()):
+    order = np.argsort(-cost, kind="stable")
+    if rot is not None and rot.any():
         # the first wave: the dearest unrotated samples; everything else by cost behind them
         r = rot[order] & (cost[order] < ROTATED_FIRST_WAVE_COST)
         head = order[~r][:FIRST_WAVE_SAMPLES]
-        taken = torch.zeros(B, dtype=torch.bool)
+        taken = np.zeros(B, bool)
         taken[head] = True
-        order = torch.cat([head, order[~taken[order]]])
-    return order.to(torch.int32)
+        order = np.concatenate([head, order[~taken[order]]])
+    return torch.from_numpy(order.astype(np.int32))
 
 
-def marshal_photo(photo: PhotoParams, B: int, device) -> Tuple[Any, List[Any]]:
-    """PhotoParams -> the C struct B200AugPhotoParams (device arrays uploaded); returns (struct, tensors to keep alive)."""
+def marshal_photo(photo: PhotoParams, B: int, device, pack: Optional[_HostPack] = None):
+    """PhotoParams -> the C struct B200AugPhotoParams (device arrays uploaded); returns (struct, tensors to keep alive).
+    With `pack` the arrays join the caller's single parameter upload and (struct, finish) is returned instead: call
+    finish(struct_in_use) after pack.upload() to fill in the pointers."""
     f32, u8 = torch.float32, torch.uint8
     p = N.PhotoParams()
     p.n_order = len(photo.order)
     for i, op in enumerate(photo.order):
         p.order[i] = int(op)
     p.clip = int(photo.clip)
-    ap = _dev(photo.apply, device, u8).reshape(B, N.NUM_OPS)
-    bi = _dev(photo.bits, device, torch.int32).reshape(B)
-    ga = _dev(photo.gamma, device, f32).reshape(B)
-    co = _dev(photo.contrast, device, f32).reshape(B)
-    br = _dev(photo.brightness, device, f32).reshape(B)
-    na = _dev(photo.noise_apply, device, u8).reshape(B, N.NUM_NOISE)
-    p.apply, p.bits, p.gamma, p.contrast, p.brightness, p.noise_apply = (t.data_ptr() for t in (ap, bi, ga, co, br, na))
+    specs = ((photo.apply, u8, (B, N.NUM_OPS)), (photo.bits, torch.int32, (B,)), (photo.gamma, f32, (B,)),
+             (photo.contrast, f32, (B,)), (photo.brightness, f32, (B,)), (photo.noise_apply, u8, (B, N.NUM_NOISE)))
+    if pack is not None:
+        toks = [pack.add(t, dt, sh) for t, dt, sh in specs]
+    else:
+        ap, bi, ga, co, br, na = (_dev(t, device, dt).reshape(sh) for t, dt, sh in specs)
+        p.apply, p.bits, p.gamma, p.contrast, p.brightness, p.noise_apply = (t.data_ptr() for t in (ap, bi, ga, co, br, na))
     for i, s in enumerate(photo.noise_std):
         p.noise_std[i] = float(s)
     for i, c in enumerate(photo.noise_clip):
         p.noise_clip[i] = int(bool(c))
     p.seed, p.sample_offset = int(photo.seed) & (2**64 - 1), int(photo.sample_offset)
+    if pack is not None:
+        def finish(target):  # (a ctypes struct is copied on assignment: fill in the copy that is launched)
+            target.apply, target.bits, target.gamma, target.contrast, target.brightness, target.noise_apply = (pack.ptr(t) for t in toks)
+            return [x for t in toks for x in pack.keep(t)]
+
+        return p, finish
     return p, [ap, bi, ga, co, br, na]
 
 
@@ -375,30 +437,23 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
 
     # ---- parameters
     f32, u8 = torch.float32, torch.uint8
+    pack = _HostPack(device)
+    late: List[Any] = []  # (setter, token): pointers filled in once the pack is on the device
     if flags & N.F_FOCUS:
         assert geo is not None
-        sc = _dev(geo.scales, device, f32).reshape(B)
-        an = _dev(geo.angles, device, f32).reshape(B)
-        tr_ = _dev(geo.translations, device, f32).reshape(B, 2)
-        keep += [sc, an, tr_]
-        args.scales, args.angles, args.translations = sc.data_ptr(), an.data_ptr(), tr_.data_ptr()
+        late += [("scales", pack.add(geo.scales, f32, (B,))), ("angles", pack.add(geo.angles, f32, (B,))),
+                 ("translations", pack.add(geo.translations, f32, (B, 2)))]
         if geo.cos_sin is not None:
-            cs = _dev(geo.cos_sin, device, f32).reshape(B, 2)
-            keep.append(cs)
-            args.cos_sin = cs.data_ptr()
+            late.append(("cos_sin", pack.add(geo.cos_sin, f32, (B, 2))))
     if flags & N.F_FLIPROT:
         if do_flip is not None:
-            df = _dev(do_flip, device, u8).reshape(B)
-            keep.append(df)
-            args.do_flip = df.data_ptr()
+            late.append(("do_flip", pack.add(do_flip, u8, (B,))))
         if rot_dir is not None:
-            rd = _dev(rot_dir, device, torch.int8).reshape(B)
-            keep.append(rd)
-            args.rot_dir = rd.data_ptr()
+            late.append(("rot_dir", pack.add(rot_dir, torch.int8, (B,))))
+    photo_finish = None
     if flags & N.F_PHOTOMETRIC:
         assert photo is not None
-        args.photo, pk = marshal_photo(photo, B, device)
-        keep += pk
+        args.photo, photo_finish = marshal_photo(photo, B, device, pack)
 
     # ---- image
     img_out = None
@@ -428,9 +483,14 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     if schedule and image_keys and B > 1:
         order = launch_order(B, geo if (flags & N.F_FOCUS) else None, photo if (flags & N.F_PHOTOMETRIC) else None)
         if order is not None:
-            od = order.to(device, non_blocking=True)
-            keep.append(od)
-            args.order = od.data_ptr()
+            late.append(("order", pack.add(order, torch.int32, (B,))))
+    # ---- one upload for all the parameter arrays
+    keep += pack.upload(torch.cuda.current_stream(device))
+    for name, tok in late:
+        setattr(args, name, pack.ptr(tok))
+        keep += pack.keep(tok)
+    if photo_finish is not None:
+        keep += photo_finish(args.photo)
     if (flags & N.F_FOCUS) and image_keys and use_workspace:
         if private_scratch:
             stride = int(N.lib.b200aug_workspace_stride(WORKSPACE_SIDE))
