@@ -865,6 +865,23 @@ __device__ __forceinline__ void hrow(uint32_t base32, const int (&xoff)[RMAX], c
   }
 }
 
+// The 2-tap kernels (cv2.resize INTER_LINEAR, or INTER_AREA with an up-scaling axis): h[j] = p0 * a0 + p1 * a1 in integers
+// (11-bit coefficients, oracle/cv2_model.py:resize_linear_u8); weights and results travel as bit patterns in the float
+// arrays of the INTER_AREA path.  The second tap is the next byte: where cv2 clamps it onto the first (frame border) its
+// weight is 0.
+__device__ __forceinline__ void hrow_linear(uint32_t base32, const int (&xoff)[RMAX], const float (&w)[RMAX][2], float (&h)[RMAX]) {
+  uint32_t px[RMAX][2];
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    const uint32_t a = base32 + (uint32_t)xoff[j];
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(px[j][0]) : "r"(a) : "memory");
+    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(px[j][1]) : "r"(a) : "memory");
+  }
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j)
+    h[j] = __int_as_float((int)px[j][0] * __float_as_int(w[j][0]) + (int)px[j][1] * __float_as_int(w[j][1]));
+}
+
 __device__ __forceinline__ uint32_t cvt_rni_sat_u8(float v) {
   uint32_t r;
   asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -894,7 +911,7 @@ __device__ __forceinline__ TileMap make_tile_map(const Plan& P, int ow, int oh) 
 //     zero padding = weight +0, so only the in-frame part of a row is ever fetched);  xbt[dx]: first tap of the column
 //     relative to its 128-column group's fetched segment.
 // (The caller checked that the CTA's canvas rows fit the program.)
-__device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band, int rows_lo, int rows_hi, int cap) {
+__device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band, int rows_lo, int rows_hi, int cap, bool linear) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(ow, oh, cap);
   const Plan& P = *reinterpret_cast<const Plan*>(smem);
@@ -907,6 +924,22 @@ __device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band,
   float* const wtab = reinterpret_cast<float*>(smem + L.off_wtab);
   int* const xbt = reinterpret_cast<int*>(wtab + (size_t)KMAX * L.wpad);
   const int tid = threadIdx.x;
+  const int cfl = max(0, -P.x0), cfh = min(P.cw, P.sw - P.x0);
+  if (linear) {
+    // 2-tap kernels: taps (x0, x0 + 1) with cv2's integer coefficients (as bit patterns); no vertical program -- the band
+    // walks cv2's row table directly
+    for (int dx = tid; dx < L.wpad; dx += NTHREADS) {
+      const bool valid = dx < ow_band;
+      const int g0 = dx & ~(32 * RMAX - 1);
+      const int dxc = valid ? dx : g0;
+      const int xs = tstart[dxc];
+      xbt[dx] = xs - max(tstart[g0], cfl);
+      const bool in0 = valid && xs >= cfl && xs < cfh, in1 = valid && xs + 1 >= cfl && xs + 1 < cfh;
+      wtab[dx] = in0 ? ta[dxc] : 0.f;              // (the bit pattern of integer 0 is +0.f)
+      wtab[L.wpad + dx] = in1 ? tb[dxc] : 0.f;
+    }
+    return;
+  }
   auto row_end = [&](int d) { return tstart[ow + d] + (tn[ow + d] & 0xffff) - 1; };
   const int Rc0 = tstart[ow + rows_lo], Rc1 = row_end(rows_hi - 1), n_rows = min(Rc1 - Rc0 + 1, NWARPS * ROWPROG_CAP);
   const float inv_sy = (float)(1.0 / P.scale_y);
@@ -929,7 +962,6 @@ __device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band,
     }
     prog[i] = make_float2(emit ? -ba : ba, bb);
   }
-  const int cfl = max(0, -P.x0), cfh = min(P.cw, P.sw - P.x0);
   for (int dx = tid; dx < L.wpad; dx += NTHREADS) {
     const bool valid = dx < ow_band;
     const int g0 = dx & ~(32 * RMAX - 1);
@@ -957,9 +989,13 @@ __device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band,
 // DIRECT: the sample's photometric chain is one point function (no equalize / blur / noise) and there is no 90-degree
 // rotation, so the finished uint8 pixel goes through the (already built) LUT straight to the float32 output `gimg` --
 // no tile, no cluster exchange, no separate output pass.
-template <int K>
+// LINEAR (K = 2): the same streaming band for cv2's 2-tap kernels -- integer horizontal pass per canvas row, and instead of
+// the vertical program the band emits, behind every canvas row r, the output rows whose second tap row is r (their first
+// tap row is r - 1 or, clamped at the border, r itself): (((b0 * (hA >> 4)) >> 16) + ((b1 * (hB >> 4)) >> 16) + 2) >> 2.
+template <int K, bool LINEAR>
 __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh, int ow_band, int warp, int lane, int cr, int cl,
                                        float* __restrict__ gimg) {
+  static_assert(!LINEAR || K == 2, "the 2-tap kernels have two taps");
   const bool DIRECT = gimg != nullptr;  // (a run-time flag: one instantiation per K keeps the hot code small)
   const int cs = 31 - __clz(cl);  // log2 of the cluster size
   const int rows_lo = (cr * oh) >> cs, rows_n = (((cr + 1) * oh) >> cs) - rows_lo;  // this CTA's band of output rows
@@ -994,9 +1030,9 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
   // (-beta_last, beta_first) must count as (beta_first, 0) here: `first_shared` patches the first entry on the fly.
   const int last = dy_end - 1;
   const int R0 = T.start[ow + dy_begin];
-  const int R1 = T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
-  const float2* const prog = reinterpret_cast<const float2*>(smem + L.off_prog) + (R0 - T.start[ow + rows_lo]);
-  const bool band_first_shared = dy_begin > rows_lo && T.start[ow + dy_begin - 1] + (T.n[ow + dy_begin - 1] & 0xffff) - 1 >= R0;
+  const int R1 = LINEAR ? T.n[ow + last] : T.start[ow + last] + (T.n[ow + last] & 0xffff) - 1;
+  const float2* const prog = reinterpret_cast<const float2*>(smem + L.off_prog) + (LINEAR ? 0 : R0 - T.start[ow + rows_lo]);
+  const bool band_first_shared = !LINEAR && dy_begin > rows_lo && T.start[ow + dy_begin - 1] + (T.n[ow + dy_begin - 1] & 0xffff) - 1 >= R0;
   const bool first_single = (T.n[ow + dy_begin] & 0xffff) == 1;  // (the shared row is the band's first output row's only tap)
   const float* const wtab = reinterpret_cast<const float*>(smem + L.off_wtab);
   const int* const xbt = reinterpret_cast<const int*>(wtab + (size_t)KMAX * L.wpad);
@@ -1007,7 +1043,7 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     const int glast = g0 + gcols - 1;
     bool first_shared = band_first_shared;  // (every column group walks the band's rows from the top)
     const int seg_lo = max(T.start[g0], cfl);
-    const int seg_hi = max(min(T.start[glast] + (T.n[glast] & 0xffff), cfh), seg_lo);
+    const int seg_hi = max(min(T.start[glast] + (LINEAR ? 2 : (T.n[glast] & 0xffff)), cfh), seg_lo);
     const int seg_bytes = seg_hi - seg_lo;
     // the lane's columns are g0 + lane + 32 j, j < nvalid; their pixels in the tile row being accumulated sit at
     // trow32 + j * cstep (shared-memory address, flip / rot90 folded in)
@@ -1034,9 +1070,10 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
       f_hi = min(R1, (last_ok ? sh - 1 : sh - 2) - y0);
       if (f_lo > f_hi) { f_lo = INT_MAX; f_hi = INT_MIN; }
     }
-    float acc[RMAX];
+    float acc[RMAX];  // INTER_AREA: the running sums | LINEAR: the previous canvas row's horizontal pass (bit patterns)
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) acc[j] = 0.f;
+    int dy_emit = dy_begin;  // LINEAR: the next output row to emit
 
     // ring state of row r: byte offset of its slot, the global address of the row's segment
     int s_off = 0;
@@ -1061,7 +1098,32 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
     };
     // vertical pass (see the program above); a fresh sum starts from +0, and 0 + x is exact
     const float2* pp = prog;
-    auto vertical = [&](const float (&h)[RMAX]) {
+    auto vertical = [&](const float (&h)[RMAX], int r) {
+      if (LINEAR) {
+        while (dy_emit < dy_end && T.n[ow + dy_emit] == r) {
+          const bool same = T.start[ow + dy_emit] == r;  // both taps on this row (clamped at the frame border)
+          const int b0 = __float_as_int(T.a[ow + dy_emit]), b1 = __float_as_int(T.b[ow + dy_emit]);
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) {
+            const int hb = __float_as_int(h[j]), ha = same ? hb : __float_as_int(acc[j]);
+            const int v = (((b0 * (ha >> 4)) >> 16) + ((b1 * (hb >> 4)) >> 16) + 2) >> 2;
+            const uint32_t q = (uint32_t)min(max(v, 0), 255);
+            if (DIRECT) {
+              float f;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(lut32 + 4u * q) : "memory");
+              if (j < nvalid) grow[j * cstep] = f;
+            } else {
+              if (j < nvalid) asm volatile("st.shared.u8 [%0], %1;" ::"r"(trow32 + (uint32_t)(j * cstep)), "r"(q) : "memory");
+            }
+          }
+          if (DIRECT) grow += row_sa;
+          else trow32 += (uint32_t)row_sa;
+          ++dy_emit;
+        }
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) acc[j] = h[j];
+        return;
+      }
       float2 pr = *pp++;
       if (first_shared) {  // (only ever true for the band's first canvas row)
         pr = make_float2(first_single ? -pr.y : pr.y, 0.f);
@@ -1129,8 +1191,9 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
           asm volatile("cp.async.wait_group 3;" ::: "memory");
           __syncwarp();  // every lane's 16 bytes of the row are in
           float h[RMAX];
-          hrow<K>(rb32 + (uint32_t)s_off + ((uint32_t)ga & 15u), xb, w, h);
-          vertical(h);
+          if (LINEAR) hrow_linear(rb32 + (uint32_t)s_off + ((uint32_t)ga & 15u), xb, reinterpret_cast<const float(&)[RMAX][2]>(w), h);
+          else hrow<K>(rb32 + (uint32_t)s_off + ((uint32_t)ga & 15u), xb, w, h);
+          vertical(h, r);
           __syncwarp();  // the slot of row r is free again: refill it with row r + D
           issue(s_off, gf, r + D <= f_hi);
           advance();
@@ -1148,9 +1211,10 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
             __syncwarp();
             stage_crop_row(P, r, seg_lo, seg_hi, rowbuf + s_off, lane);
             __syncwarp();
-            hrow<K>(rb32 + (uint32_t)s_off, xb, w, h);
+            if (LINEAR) hrow_linear(rb32 + (uint32_t)s_off, xb, reinterpret_cast<const float(&)[RMAX][2]>(w), h);
+            else hrow<K>(rb32 + (uint32_t)s_off, xb, w, h);
           }
-          vertical(h);
+          vertical(h, r);
           __syncwarp();
           issue(s_off, gf, r + D >= f_lo && r + D <= f_hi);
           advance();
@@ -1905,9 +1969,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   // columns [0, ow_band) are resampled by the warps' bands, a short last group by the per-pixel path
   const int ow_tail = ow % (32 * RMAX);
   const int ow_band = (ow_tail != 0 && ow_tail <= TAIL_COLS) ? ow - ow_tail : ow;
-  bool fast = (P.status == B200AUG_S_OK) && (rs == RS_AREA || rs == RS_AREA_INT) && (P.kx <= KMAX) && (P.src_mode != SRC_WARP) &&
+  const bool lin = rs == RS_LINEAR;  // cv2's 2-tap kernels stream through the same bands
+  bool fast = (P.status == B200AUG_S_OK) && (((rs == RS_AREA || rs == RS_AREA_INT) && P.kx <= KMAX) || lin) && (P.src_mode != SRC_WARP) &&
               ow_band > 0;
-  if (fast) {
+  if (fast && !lin) {
     // the CTA's canvas rows must fit its vertical-pass program
     // (the widest share of any CTA of the cluster: `fast` -- and with it `direct` -- must come out the same in all of them)
     const int rows_per_cta = ((oh + cl - 1) >> cs) + 1;
@@ -1918,23 +1983,24 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     // every column group's canvas segment must fit the per-warp row buffer (only staged rows need it)
     for (int g0 = 0; g0 < ow_band; g0 += 32 * RMAX) {
       const int glast = min(g0 + 32 * RMAX, ow_band) - 1;
-      const int seg = T.start[glast] + (T.n[glast] & 0xffff) - T.start[g0];
+      const int seg = T.start[glast] + (lin ? 2 : (T.n[glast] & 0xffff)) - T.start[g0];
       if (RING_D * ring_slot_bytes(seg) > cap + ROWBUF_SLACK || seg + 30 > 64 * 16) fast = false;
     }
   }
   // direct: no tile, no exchange, no output pass -- the resampling pass writes the float32 crop itself
-  const bool direct = fast && lut_early && rs == RS_AREA && P.fin == 0 && P.rot_dir == 0;
+  const bool direct = fast && lut_early && ((rs == RS_AREA && P.fin == 0) || lin) && P.rot_dir == 0;
   // Every CTA of the cluster must be running (its exchange barrier initialised) before the tile exchange touches its shared
   // memory: arrive now, wait only in front of the exchange -- the resampling in between never waits for the partner.
   // (direct samples have no exchange; `direct` comes out the same in all CTAs of the cluster.)
   if (cl > 1 && !direct) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   if (fast) {
     const int kx = P.kx;
-    area_precompute(kx <= 3 ? 3 : (kx == 4 ? 4 : 6), ow, oh, ow_band, rows_lo, rows_hi, cap);
+    area_precompute(kx <= 3 ? 3 : (kx == 4 ? 4 : 6), ow, oh, ow_band, rows_lo, rows_hi, cap, lin);
     __syncthreads();
     float* const gimg = direct ? a.image_f32_out + (size_t)b * npix : nullptr;
-#define B200AUG_BAND(KK) area_band<KK>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg)
-    if (kx <= 3) B200AUG_BAND(3);
+#define B200AUG_BAND(KK) area_band<KK, false>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg)
+    if (lin) area_band<2, true>(tm, cap, ow, oh, ow_band, warp, lane, cr, cl, gimg);
+    else if (kx <= 3) B200AUG_BAND(3);
     else if (kx == 4) B200AUG_BAND(4);
     else B200AUG_BAND(6);
 #undef B200AUG_BAND
@@ -1973,7 +2039,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
     } else {
       for (int p = tid; p < (rows_hi - rows_lo) * tw; p += NTHREADS) {
         const int dy = rows_lo + p / tw, dx = ow_band + p % tw;
-        tile[tm.o + dy * tm.sa + dx * tm.sb] = scalar_out_px(P, T, ow, dx, dy);
+        const uint8_t q = scalar_out_px(P, T, ow, dx, dy);
+        if (direct) gimg[tm.o + dy * tm.sa + dx * tm.sb] = lut[q];
+        else tile[tm.o + dy * tm.sa + dx * tm.sb] = q;
       }
     }
   } else if (P.status == B200AUG_S_OK && rs == RS_LINEAR && P.src_mode != SRC_WARP) {

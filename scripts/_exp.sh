@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python scripts/host_profile.py 2>&1 | head -22
-timeout 300 python scripts/train_bench.py --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k: d[k] for k in ('samples_per_s','ms_per_step','ms_train_only','ms_aug_from_pinned_host','overhead_of_aug_when_overlapped_ms')})"
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python scripts/gpu_stress.py 8 2>&1 | tail -2
+timeout 300 python scripts/localizer_bench.py 2>&1 | tail -1
+timeout 200 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --quick 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('step %.1f us' % (d['ms_per_step']*1e3))"

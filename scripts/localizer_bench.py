@@ -30,8 +30,13 @@ def main():
     from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
     from trackertraincode_b200.datatransformation import _engine as E
 
-    dev = torch.device("cuda", 0)
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:  # per-sample sharding, one process per GPU, no collective on the data path (weak scaling: 256 frames per GPU)
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
     flags = N.F_FOCUS | N.F_FLIPROT | N.F_NORMALIZE | N.F_PHOTOMETRIC | N.F_WHITEN
     calls, alg = [], []
     for r in range(RING):
@@ -64,12 +69,22 @@ def main():
         st = c_.result.status.cpu().numpy()
         assert not st.any(), f"per-sample status {np.unique(st)}"
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     e0.record()
     for s in range(args.steps):
         calls[s % RING].launch()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / args.steps * 1e3
+    if world > 1:
+        t = torch.tensor([us], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     peak = 6650.0
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -77,8 +92,8 @@ def main():
         pass
     gbs = float(np.mean(alg)) / (us * 1e-6) / 1e9
     print(json.dumps({"config": f"configs[4] shape: {B} x {W}x{H} u8 gray -> {OW}x{OH} f32, ROI crop + flip + photometric + whiten + roi label, ring of "
-                                f"{RING} batches ({RING * B * W * H / 1e6:.0f} MB of sources), 1 B200",
-                      "kernel_us": us, "samples_per_s": B / (us * 1e-6), "algorithmic_bytes_per_launch": float(np.mean(alg)),
+                                f"{RING} batches ({RING * B * W * H / 1e6:.0f} MB of sources), {world} x B200 (256 frames per GPU, no collective)",
+                      "n_gpus": world, "kernel_us": us, "samples_per_s": world * B / (us * 1e-6), "algorithmic_bytes_per_launch": float(np.mean(alg)),
                       "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak}))
 
 
