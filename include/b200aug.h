@@ -267,6 +267,8 @@ int b200aug_jpeg_info(const uint8_t* data, size_t length, int32_t* width, int32_
 int b200aug_decode_jpeg_gray(const uint8_t* const* data, const size_t* lengths, int32_t batch, uint8_t* const* dst,
                              const int32_t* pitch, void* stream);
 int b200aug_jpeg_last_status(void);
+/* 0 = nvJPEG unavailable, 1 = hybrid GPU backend, 2 = the NVJPG hardware engines (env B200AUG_JPEG_BACKEND=hardware) */
+int b200aug_jpeg_backend(void);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,8 @@
 #include <nvjpeg.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "b200aug.h"
@@ -21,12 +23,21 @@ struct JpegCtx {
   int batch = 0;      // batch size the state is initialised for
   int status = 0;     // last nvjpegStatus_t that failed
   bool ok = false;
+  bool hardware = false;
 };
 
 JpegCtx& ctx() {
   static thread_local JpegCtx c;
   if (!c.handle) {
-    nvjpegStatus_t s = nvjpegCreateEx(NVJPEG_BACKEND_GPU_HYBRID, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &c.handle);
+    // backend: the GPU's NVJPG engines when B200AUG_JPEG_BACKEND=hardware (and the library accepts it), else nvJPEG's hybrid
+    // decoder (Huffman decoding on host threads, IDCT on the SMs)
+    const char* be = getenv("B200AUG_JPEG_BACKEND");
+    nvjpegStatus_t s = NVJPEG_STATUS_NOT_INITIALIZED;
+    if (be && be[0] == 'h') {
+      s = nvjpegCreateEx(NVJPEG_BACKEND_HARDWARE, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &c.handle);
+      c.hardware = (s == NVJPEG_STATUS_SUCCESS);
+    }
+    if (s != NVJPEG_STATUS_SUCCESS) s = nvjpegCreateEx(NVJPEG_BACKEND_GPU_HYBRID, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &c.handle);
     if (s != NVJPEG_STATUS_SUCCESS) s = nvjpegCreateSimple(&c.handle);
     if (s == NVJPEG_STATUS_SUCCESS) s = nvjpegJpegStateCreate(c.handle, &c.state);
     c.status = (int)s;
@@ -38,6 +49,8 @@ JpegCtx& ctx() {
 }  // namespace
 
 extern "C" int b200aug_jpeg_last_status(void) { return ctx().status; }
+
+extern "C" int b200aug_jpeg_backend(void) { return ctx().ok ? (ctx().hardware ? 2 : 1) : 0; }
 
 extern "C" int b200aug_jpeg_info(const uint8_t* data, size_t length, int32_t* width, int32_t* height, int32_t* components) {
   if (!data || !length || !width || !height) return B200AUG_E_INVALID_ARG;
@@ -61,7 +74,13 @@ extern "C" int b200aug_decode_jpeg_gray(const uint8_t* const* data, const size_t
   if (!c.ok) return B200AUG_E_CUDA;
   nvjpegStatus_t s;
   if (c.batch != batch) {
-    s = nvjpegDecodeBatchedInitialize(c.handle, c.state, batch, 1, NVJPEG_OUTPUT_Y);
+    // the hybrid backend decodes the entropy-coded segments on host threads: give it the cores this process may use
+    static const int n_threads = [] {
+      const char* e = getenv("B200AUG_JPEG_THREADS");
+      int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+      return n < 1 ? 1 : (n > 32 ? 32 : n);
+    }();
+    s = nvjpegDecodeBatchedInitialize(c.handle, c.state, batch, n_threads, NVJPEG_OUTPUT_Y);
     if (s != NVJPEG_STATUS_SUCCESS) { c.status = (int)s; c.batch = 0; return B200AUG_E_CUDA; }
     c.batch = batch;
   }
