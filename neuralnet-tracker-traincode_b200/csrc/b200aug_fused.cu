@@ -1,22 +1,24 @@
-// Fused augmentation kernel for sm_100a: one CTA per sample does
-//   label transforms -> crop / warp resample (OpenCV-exact) -> flip/rot90 -> normalise -> photometric chain -> whiten
+// The augmentation kernels for sm_100a (include/b200aug.h: b200aug_fused_forward):
+//   plan_kernel            one small CTA per sample: view box / transforms / cv2 resize tables / ALL label transforms
+//   fused_augment_kernel   canvas workers (cv2.warpAffine of the rotated samples into an L2-resident canvas, a work-stealing
+//                          role taken by some CTAs of the grid) + one 2-CTA cluster per sample:
+//                          crop / canvas -> cv2.resize (OpenCV-exact) -> flip/rot90 -> normalise -> photometric chain -> whiten
 // reading each source byte once from HBM and writing the float32 crop once.
 //
 // Pixel path (the specification is oracle/cv2_model.py, pinned bit-exact against cv2).  The "canvas" is the image
 // cv2.resize sees: the zero-padded integer crop (image_geometric_cv2.py:28-44) or the output of cv2.warpAffine
-// (INTER_LINEAR fixed point: 1/32 px coordinates, 15-bit weights).  It never exists in memory:
-//   fast path  cv2.resize INTER_AREA with a non-integer factor (what training and evaluation produce): each warp owns
-//              a band of output rows and streams the canvas rows that feed it once, in order.  Crop rows inside the
-//              frame are read straight from global memory as aligned 32-bit words (every source byte is requested
-//              once per CTA; neighbouring lanes share sectors); rows on the frame border and warp rows are staged in a
-//              per-warp shared-memory row.  The lane keeps its columns' tap weights in registers (dense, zero padded),
-//              does the float32 horizontal pass and accumulates the vertical pass in table order.
-//   per-pixel  everything else (integer-factor INTER_AREA, INTER_LINEAR up-scaling, plain copy, extreme sizes) goes
-//              through scalar_out_px(), the straight restatement of the model.
+// (INTER_LINEAR fixed point: 1/32 px coordinates, 15-bit weights).  A crop's canvas never exists in memory:
+//   fast path  cv2.resize INTER_AREA with a non-integer factor (what training and evaluation produce), and cv2's 2-tap
+//              kernels: each warp owns a band of output rows and streams the canvas rows that feed it once, in order,
+//              through a per-warp cp.async ring in shared memory.  The lane keeps its columns' tap weights in registers
+//              (dense, zero padded), does the float32 horizontal pass and accumulates the vertical pass in table order.
+//   per-pixel  everything else (integer-factor INTER_AREA, plain copy, extreme sizes) goes through scalar_out_px(), the
+//              straight restatement of the model.
 // The uint8 crop lands in a shared-memory tile (flip/rot90 applied by the store address).  The stage-1 photometric
 // ops are point functions of the uint8 value, so they collapse into a 256-entry LUT per sample (equalize's histogram
 // is the uint8 histogram pushed through the LUT prefix); only the 5x5 blur needs neighbours.  The output pass streams
-// the tile through LUT [+blur] [+noise, Philox] [+clip] [-0.5] into coalesced float32 stores.
+// the tile through LUT [+blur] [+noise, Philox] [+clip] [-0.5] into coalesced float32 stores; samples whose chain is a
+// single point function skip tile and output pass (direct mode).
 #include <cuda_runtime.h>
 #include <vector>
 #include <cstdlib>
@@ -714,134 +716,6 @@ __device__ __forceinline__ int stage_crop_row(const Plan& P, int y, int lo, int 
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ warpAffine, tile-staged
-
-constexpr int WT_W = 32, WT_H = 16;     // canvas tile of one warp iteration
-constexpr int WT_STRIDE = 64;           // staged source row: <= 38 px of bounding box + 15 B alignment shift, in 16 B chunks
-constexpr int WT_ROWS = 39;             // tallest bounding box of a 32 x 16 tile under any rotation at unit scale, + taps
-
-// cv2.warpAffine of the whole canvas into `scratch` (global memory, stays in L2; row pitch `spitch`), one 32 x 16 canvas
-// tile per warp iteration.  The canvas has the resolution of the source (image_geometric_cv2.py:121-124 sizes it so), so a
-// tile's source footprint is a rotated 32 x 16 rectangle: its bounding box (<= 39 rows x 38 px) is staged in the warp's
-// shared-memory area with 16-byte loads and the four bilinear taps of every pixel are gathered from there -- a gather
-// straight from global memory would touch ~16 cache lines per warp instruction.  Tiles whose bounding box leaves the
-// frame (BORDER_CONSTANT zeros) or is too large (a down-scaling canvas never is) take the predicated global path.
-__device__ void warp_canvas_to_scratch(const Plan& P, const int2* __restrict__ dtab, uint8_t* stage, int stage_bytes,
-                                       uint8_t* __restrict__ scratch, int spitch, int warp, int lane, int cr, int cl) {
-  const uint8_t* __restrict__ src = P.src;
-  const int pitch = P.pitch, sw = P.sw, sh = P.sh, cw = P.cw, ch = P.ch;
-  const double m1 = P.mi[1], m2 = P.mi[2], m4 = P.mi[4], m5 = P.mi[5];
-  const int tiles_x = (cw + WT_W - 1) / WT_W, tiles_y = (ch + WT_H - 1) / WT_H;
-  const uint32_t stage32 = smem_u32(stage);
-  const int pm = pitch & 15;
-  auto row_origin = [&](int y, int& X0, int& Y0) {
-    X0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
-    Y0 = rint_d2i(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
-  };
-  // Row stride of the staged box: WT_STRIDE + pm or WT_STRIDE + 16 + pm bytes, whichever spreads one canvas row's 32 taps
-  // over more shared-memory banks.  The taps walk a straight line (mi[0] px right, mi[3] px down per canvas pixel), so the
-  // bank pattern depends on slope and stride only: at pitch 450 (pm = 2) and -30 degrees a 66-byte stride makes lanes two
-  // rows apart land 16 words apart -- 7 wavefronts per byte load -- while 82 bytes gives 2 (and 66 gives 1 at +30 degrees).
-  int wt_stride = WT_STRIDE;
-  {
-    const int ix = (int)floor(P.mi[0] * (double)lane), iy = (int)floor(P.mi[3] * (double)lane) + 64;
-    int best = INT_MAX;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int e = WT_STRIDE + 16 * c + pm;
-      const unsigned word = (unsigned)(iy * e + ix) >> 2, bank = word & 31u;
-      const unsigned same_word = __match_any_sync(0xffffffffu, word), same_bank = __match_any_sync(0xffffffffu, bank);
-      const unsigned leaders = __ballot_sync(0xffffffffu, (__ffs(same_word) - 1) == lane);  // one lane per distinct word
-      const int degree = __reduce_max_sync(0xffffffffu, __popc(same_bank & leaders));      // wavefronts of this load
-      if (degree < best) { best = degree; wt_stride = WT_STRIDE + 16 * c; }
-    }
-  }
-  for (int t = cr * NWARPS + warp; t < tiles_x * tiles_y; t += cl * NWARPS) {
-    const int ty = t / tiles_x, tx = t - ty * tiles_x;
-    const int x_lo = tx * WT_W, y_lo = ty * WT_H;
-    const int tw = min(WT_W, cw - x_lo), th = min(WT_H, ch - y_lo);
-    // bounding box of the taps from the four tile corners (the fixed-point map is monotone in x and in y)
-    int Xa, Ya, Xb, Yb;
-    row_origin(y_lo, Xa, Ya);
-    row_origin(y_lo + th - 1, Xb, Yb);
-    const int2 dl = dtab[x_lo], dr = dtab[x_lo + tw - 1];
-    const int ix0 = (Xa + dl.x) >> 10, ix1 = (Xa + dr.x) >> 10, ix2 = (Xb + dl.x) >> 10, ix3 = (Xb + dr.x) >> 10;
-    const int iy0 = (Ya + dl.y) >> 10, iy1 = (Ya + dr.y) >> 10, iy2 = (Yb + dl.y) >> 10, iy3 = (Yb + dr.y) >> 10;
-    const int bx0 = min(min(ix0, ix1), min(ix2, ix3)), bx1 = max(max(ix0, ix1), max(ix2, ix3)) + 1;
-    const int by0 = min(min(iy0, iy1), min(iy2, iy3)), by1 = max(max(iy0, iy1), max(iy2, iy3)) + 1;
-    const int nrows = by1 - by0 + 1;
-    // Staged layout: box row r is copied as four 16-byte chunks starting at the aligned address at or below its first byte,
-    // to shared-memory offset S_r = B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift of row 0, pm = pitch mod 16, B = 64 or
-    // 80.  The byte of box row r, box column x then sits at c0 + r (B + pm) + x: linear in r, so the gather needs no per-row shift.
-    const uintptr_t gbase = reinterpret_cast<uintptr_t>(src) + (size_t)by0 * pitch + bx0;  // top-left of the box
-    const int c0 = (int)(gbase & 15);
-    auto fits = [&](int st) { return (nrows - 1) * st + 16 * ((c0 + (nrows - 1) * pm) >> 4) + WT_STRIDE <= stage_bytes; };
-    const int bstride = fits(wt_stride) ? wt_stride : WT_STRIDE;  // (a tall box falls back to the compact stride)
-    const int rstride = bstride + pm;
-    // staged: inside the frame (and not on its last row: the 16-byte chunks may run past a row's end), small enough
-    const bool staged = bx0 >= 0 && bx1 < sw && by0 >= 0 && by1 < sh - 1 && nrows <= WT_ROWS && (bx1 - bx0 + 1) + 15 <= WT_STRIDE &&
-                        fits(bstride);
-    __syncwarp();
-    if (staged) {
-      // item = (row, 16-byte chunk); all loads first, then the stores
-      uint4 v[5];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int item = lane + 32 * i, row = item >> 2, k = item & 3;
-        if (row < nrows) {
-          const uintptr_t g = (gbase + (size_t)row * pitch) & ~uintptr_t(15);
-          v[i] = __ldg(reinterpret_cast<const uint4*>(g) + k);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int item = lane + 32 * i, row = item >> 2, k = item & 3;
-        if (row < nrows) *reinterpret_cast<uint4*>(stage + row * bstride + 16 * ((c0 + row * pm) >> 4) + 16 * k) = v[i];
-      }
-      __syncwarp();
-      int X0l, Y0l;                      // lane yy holds the row origin of tile row yy
-      row_origin(y_lo + min(lane, th - 1), X0l, Y0l);
-      const int2 d = dtab[x_lo + min(lane, tw - 1)];
-      // shared-memory address of source pixel (iy, ix) = tap0 + iy * rstride + ix
-      const uint32_t tap0 = stage32 + (uint32_t)(c0 - bx0 - by0 * rstride);
-      uint8_t* out = scratch + (size_t)y_lo * spitch + x_lo + lane;
-      const bool act = lane < tw;  // (idle lanes repeat the last column: their addresses stay valid)
-#pragma unroll 4
-      for (int yy = 0; yy < th; ++yy) {
-        const int sx = __shfl_sync(0xffffffffu, X0l, yy) + d.x, sy = __shfl_sync(0xffffffffu, Y0l, yy) + d.y;  // 1/1024 px
-        const uint32_t a0 = tap0 + (uint32_t)((sy >> 10) * rstride + (sx >> 10)), a1 = a0 + (uint32_t)rstride;
-        uint32_t p00, p01, p10, p11;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a0) : "memory");
-        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(a0) : "memory");
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a1) : "memory");
-        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p11) : "r"(a1) : "memory");
-        const int q = bilinear_q5((int)p00, (int)p01, (int)p10, (int)p11, (sx >> 5) & 31, (sy >> 5) & 31);
-        if (act) *out = (uint8_t)q;
-        out += spitch;
-      }
-    } else if (lane < tw) {
-      const int2 d = dtab[x_lo + lane];
-      uint8_t* out = scratch + (size_t)y_lo * spitch + x_lo + lane;
-      for (int yy = 0; yy < th; ++yy) {
-        int X0, Y0;
-        row_origin(y_lo + yy, X0, Y0);
-        const int X = (X0 + d.x) >> 5, Y = (Y0 + d.y) >> 5;
-        const int ix = X >> 5, iy = Y >> 5;
-        const bool r0 = (unsigned)iy < (unsigned)sh, r1 = (unsigned)(iy + 1) < (unsigned)sh;
-        const bool c0 = (unsigned)ix < (unsigned)sw, c1 = (unsigned)(ix + 1) < (unsigned)sw;
-        const uint8_t* p = src + (ptrdiff_t)iy * pitch + ix;
-        const int p00 = (r0 && c0) ? __ldg(p) : 0;
-        const int p01 = (r0 && c1) ? __ldg(p + 1) : 0;
-        const int p10 = (r1 && c0) ? __ldg(p + pitch) : 0;
-        const int p11 = (r1 && c1) ? __ldg(p + pitch + 1) : 0;
-        out[(size_t)yy * spitch] = (uint8_t)bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
-      }
-    }
-  }
-  // the canvas is read back through the async proxy (bulk copies): order these generic-proxy writes before it
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
-
 // ------------------------------------------------------------------------------------------------ INTER_AREA fast path
 
 // Horizontal pass of one staged canvas row for the lane's columns: h[j] = sum_t w[j][t] * S[xoff[j] + t], taps in table
@@ -985,7 +859,7 @@ __device__ __noinline__ void area_precompute(int K, int ow, int oh, int ow_band,
 // 16-byte vectors per row: the aligned superset of the row segment).  The band is walked in three phases so that the
 // steady state carries no row classification: rows above the frame (zeros) / the fetched rows / rows below the frame or
 // the frame's last row when its over-read would leave the image (staged synchronously, zero padded).
-// The canvas is always a crop here: rotated samples were turned into one by warp_canvas_to_scratch().
+// The canvas is always a crop here: rotated samples were turned into one by the canvas workers.
 // DIRECT: the sample's photometric chain is one point function (no equalize / blur / noise) and there is no 90-degree
 // rotation, so the finished uint8 pixel goes through the (already built) LUT straight to the float32 output `gimg` --
 // no tile, no cluster exchange, no separate output pass.
@@ -1526,7 +1400,7 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
 // gathered, so the loads' latency never sits in front of the arithmetic.  Box rows outside the frame are zero-filled by the
 // copy itself (src-size 0 = BORDER_CONSTANT), columns outside it by a fix-up pass over the staged box, so the gather loop
 // is the same for every tile: per 32 pixels 2 adds, 3 address ops, 4 byte loads, the 11-op fixed-point blend, 1 store.
-// Staged layout (as warp_canvas_to_scratch): box row r lands at offset B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift
+// Staged layout: box row r lands at offset B r + 16 ((c0 + r pm) >> 4), c0 = alignment shift
 // of row 0, pm = pitch mod 16, so that source pixel (iy, ix) sits at c0 + (iy - by0)(B + pm) + (ix - bx0): linear, no
 // per-row alignment fix-up in the gather; B is 96 or 112, whichever spreads one canvas row's taps over more banks.
 #ifndef B200AUG_WK_CHUNKS

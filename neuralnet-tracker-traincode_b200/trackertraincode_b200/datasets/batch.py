@@ -83,7 +83,14 @@ def _cat(items):
     if isinstance(first, np.ndarray):
         return np.concatenate(list(items), axis=0)
     if isinstance(first, list):  # ragged image lists concatenate as lists
-        return [x for it in items for x in it]
+        flat = [x for it in items for x in it]
+        if flat and all(isinstance(x, torch.Tensor) and x.dim() == 1 and x.dtype == torch.uint8 for x in flat):
+            # encoded blobs (JPEG bytes of different lengths): ONE buffer, the list holds views of it -- a DataLoader worker
+            # then ships one shared-memory segment per batch instead of one per sample
+            packed = torch.cat(flat)
+            ends = np.cumsum([int(x.numel()) for x in flat])
+            return [packed[e - int(x.numel()):e] for x, e in zip(flat, ends)]
+        return flat
     raise TypeError(f"cannot collate {type(first)}")
 
 
