@@ -185,6 +185,21 @@ def test_loader_glue_ragged_segmented():
     assert len(items) == 10 and items[3].meta.tag == "odd"
 
 
+def test_loader_lookahead_keeps_order_and_runs_ahead():
+    from trackertraincode_b200.datatransformation import PostprocessingLoader
+    issued = []
+    ld = PostprocessingLoader(list(range(12)), batch_size=3, postprocess=lambda t: issued.append(int(t[0])) or t, lookahead=2)
+    assert len(ld) == 4 and ld.dataset == list(range(12))
+    it = iter(ld)
+    first = next(it)
+    assert first.tolist() == [0, 1, 2] and issued == [0, 3, 6]  # two groups already went through the hook
+    assert [t.tolist()[0] for t in it] == [3, 6, 9] and issued == [0, 3, 6, 9]
+    plain = PostprocessingLoader(list(range(4)), batch_size=2)  # no hook: items pass through
+    assert [t.tolist() for t in plain] == [[0, 1], [2, 3]]
+    with pytest.raises(TypeError):
+        list(SegmentedCollationDataLoader.__new__(SegmentedCollationDataLoader)._emit(3))
+
+
 def test_sharding_helpers_single_process():
     for n, w in [(512, 8), (10, 3), (7, 8)]:
         r = [sharding.shard_range(n, k, w) for k in range(w)]
