@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200AUG_ABI_VERSION 6
+#define B200AUG_ABI_VERSION 7
 
 /* error codes */
 #define B200AUG_OK 0
@@ -41,7 +41,8 @@ extern "C" {
 /* per-sample status codes written to status_out */
 #define B200AUG_S_OK 0
 #define B200AUG_S_EMPTY_BOX 1     /* view box with non-positive width/height (cv2.resize would throw) */
-#define B200AUG_S_UNSUPPORTED 2   /* reserved (INTER_AREA with an up-scaling axis is handled since ABI 4: cv2's 2-tap area-mode path) */
+#define B200AUG_S_UNSUPPORTED 2   /* an anti-alias prefilter wider than B200AUG_PREFILTER_MAX_TAPS (scale below ~0.05), or a
+                                     prefiltered canvas that does not fit its workspace region: the image is zeros */
 #define B200AUG_S_ROWBUF 3        /* reserved (ABI 1 reported row-buffer overflow; since ABI 2 such samples take the per-pixel path) */
 
 /* field categories: FieldCategory, trackertraincode/datasets/dshdf5pose.py:21-28 */
@@ -66,6 +67,16 @@ extern "C" {
                                               same call compose onto it; written to backtransform_out */
 
 /* B200AugFusedArgs::phase */
+/* B200AugFusedArgs::downfilter -- DownFilters of tensors/image_geometric_cv2.py:15, used when a crop shrinks (:65-82):
+ * "area" = cv2.resize(INTER_AREA); the other two smooth the canvas first (_apply_antialias_filter, :47-62) and resize it
+ * with INTER_LINEAR */
+#define B200AUG_DOWN_AREA 0
+#define B200AUG_DOWN_GAUSSIAN 1   /* the reference's cv2.GaussianBlur call as Python binds its positional arguments (:50):
+                                     sigmaX = 0.5 / scale, sigmaY = 1, BORDER_REFLECT_101; 8-bit fixed point, bit-exact */
+#define B200AUG_DOWN_HAMMING 2    /* cv2.sepFilter2D with the normalised Hamming window of round(2 / scale + 1) taps (made
+                                     odd): float32, the arithmetic of cv2's vector loops */
+#define B200AUG_PREFILTER_MAX_TAPS 63
+
 #define B200AUG_PHASE_ALL 0
 #define B200AUG_PHASE_PLAN 1
 #define B200AUG_PHASE_MAIN 2
@@ -174,14 +185,14 @@ typedef struct B200AugFusedArgs {
   const int32_t* order;
   /* optional scratch for rotated samples: B regions of workspace_stride bytes (see b200aug_workspace_stride()).  The
    * two-stage rotated path (warpAffine canvas, then INTER_AREA; image_geometric_cv2.py:121-134) keeps its canvas here,
-   * i.e. in L2: a kernel of its own (warp_kernel, needs `plans` too) fills the canvases while the fused kernel already
-   * resamples the unrotated samples.  Without it (NULL) or when a canvas does not fit, canvas pixels are produced one at a
-   * time instead. */
+   * i.e. in L2: some CTAs of the fused grid ("canvas workers", needs `plans` too) fill the canvases while the others already
+   * resample the unrotated samples.  Without it (NULL) or when a canvas does not fit, canvas pixels are produced one at a
+   * time instead.  Anti-alias prefilters (downfilter) keep their smoothed canvases here as well. */
   uint8_t* workspace;
   int64_t workspace_stride;
   /* optional scratch for the plans: b200aug_plan_buffer_bytes(batch, out_w, out_h) bytes = B records of plan_stride bytes
    * (= b200aug_plan_stride(out_w, out_h), a multiple of 16) followed by a small tail (work counters and per-sample flags
-   * of warp_kernel).  A small kernel computes every sample's plan, cv2 resize tables and LABELS first (it always runs: the
+   * of the canvas workers).  A small kernel computes every sample's plan, cv2 resize tables and LABELS first (it always runs: the
    * labels are its output); with this buffer it also leaves the records for the fused kernel to load, instead of every CTA
    * rebuilding them behind its full register / shared-memory footprint.  NULL = build them inside the fused kernel. */
   uint8_t* plans;
@@ -193,6 +204,16 @@ typedef struct B200AugFusedArgs {
                                    left in `plans`).  A caller that pipelines steps runs PLAN of step s + 1 on a second stream
                                    next to MAIN of step s: plan_kernel is a short latency-bound grid that fits into the tail of
                                    the big kernel. */
+
+  int32_t downfilter;           /* B200AUG_DOWN_*; anything but AREA needs `plans` and `workspace` (else E_UNSUPPORTED) */
+  int32_t reserved0;
+  /* B200AUG_DOWN_HAMMING: the normalised Hamming windows as float32, row r = (n - 1) / 2 of a [32][64] device table holds
+   * the n = 2 r + 1 taps (scipy.signal.windows.hamming(n) / sum, evaluated on the host exactly as the reference does and
+   * then rounded to float32, as cv2 does); bit r of hamming_sym_mask says whether the float64 window is exactly mirror
+   * symmetric, which is what makes cv2 pick its symmetric column filter (that depends on the host's cos(), so the caller
+   * decides).  b200aug_hamming_table() fills both from a given evaluation of the windows. */
+  const float* hamming_taps;
+  uint64_t hamming_sym_mask;
 
   B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
 } B200AugFusedArgs;
@@ -208,6 +229,10 @@ int64_t b200aug_workspace_stride(int max_side);
 /* bytes of one record of B200AugFusedArgs::plans for this output size, and of the whole buffer for `batch` samples */
 int64_t b200aug_plan_stride(int out_w, int out_h);
 int64_t b200aug_plan_buffer_bytes(int batch, int out_w, int out_h);
+/* Packs Hamming windows for B200AugFusedArgs::hamming_taps: windows = HOST float64, the normalised window of n = 2 r + 1
+ * taps at windows[r * 64 .. r * 64 + n) for r = 1 .. 31 (row 0 unused); taps_out = HOST float32 [32 * 64] (copy it to the
+ * device), *sym_mask_out = the symmetry bits.  Plain host code, no CUDA call. */
+int b200aug_hamming_table(const double* windows, float* taps_out, uint64_t* sym_mask_out);
 
 /* Host -> device upload of the rows the fused kernel will read, instead of whole frames (Batch.to(device),
  * datasets/batch.py:161-165 / pipelines.py:508): for each of `batch` stacked frames (host_frames: PINNED host memory,
@@ -217,10 +242,13 @@ int64_t b200aug_plan_buffer_bytes(int batch, int out_w, int out_h);
 int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
                              int32_t batch, const int32_t* row_lo, const int32_t* row_hi, void* stream);
 
-/* The fused hot path.  Up to three kernels, chained with programmatic dependent launches on `stream`:
+/* The fused hot path.  Two kernels (three with an anti-alias prefilter) on `stream`, the second behind a programmatic
+ * dependent launch:
  *   plan_kernel   one small CTA per sample: view box, transforms, cv2 resize tables, all label transforms, side outputs
- *   warp_kernel   (rotated samples, needs plans + workspace) cv2.warpAffine canvases, persistent work-stealing grid
- *   fused_augment_kernel   one cluster per sample: cv2.resize -> flip/rot90 -> normalise -> photometric chain -> whiten
+ *   prefilter_kernel   (downfilter gaussian / hamming only) the smoothed canvases of the down-scaled samples
+ *   fused_augment_kernel   one cluster per sample: cv2.resize -> flip/rot90 -> normalise -> photometric chain -> whiten;
+ *                 plus the canvas workers (rotated samples, needs plans + workspace): CTAs of the same grid that produce the
+ *                 cv2.warpAffine canvases, handing out work items through an atomic counter
  * A call without an image output (labels only) runs plan_kernel alone.
  * Replaces, per the flags: batch/normalization.py:83-90, batch/misc.py:9-31, batch/geometric.py:107-231
  * (+ tensors/image_geometric_cv2.py:28-155 incl. cv2.warpAffine / cv2.resize arithmetic, tensors/affinetrafo.py:37-148),

@@ -86,6 +86,11 @@ struct Plan {
   uint8_t* cv_ptr;
   int cv_pitch;
   int cv_pad;
+  // anti-alias prefilter (downfilter gaussian / hamming, image_geometric_cv2.py:47-62): prefilter_kernel leaves the smoothed
+  // canvas at cv_ptr, the resize is then cv2's INTER_LINEAR.  0 = none, else B200AUG_DOWN_*; pf_n taps; pf_sf = the mean
+  // scale factor the taps derive from
+  int prefilter, pf_n;
+  double pf_sf;
 };
 
 constexpr size_t WORKER_AREA = 2 * 512 * 8 + 1024 * 2 + 128 + 32 * 48 + 3 * 9136;  // = WK_AREA_BYTES (checked where that is defined)
@@ -130,6 +135,15 @@ struct KArgs {
 };
 
 __device__ __forceinline__ int rint_d2i(double v) { return __double2int_rn(v); }
+
+// taps cv2.GaussianBlur derives from sigma for 8-bit images (ksize (0, 0))
+__host__ __device__ __forceinline__ int gaussian_ksize_u8(double sigma) {
+#ifdef __CUDA_ARCH__
+  return __double2int_rn(sigma * 3.0 * 2.0 + 1.0) | 1;
+#else
+  return (int)nearbyint(sigma * 3.0 * 2.0 + 1.0) | 1;
+#endif
+}
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
@@ -366,6 +380,9 @@ __device__ void plan_resize(const B200AugFusedArgs& a, const PlanCore& c, Plan& 
   P.status = B200AUG_S_OK;
   P.fin = 0;
   P.lin_area = 0;
+  P.prefilter = 0;
+  P.pf_n = 0;
+  P.pf_sf = 1.0;
   if (c.cw <= 0 || c.ch <= 0) {
     P.status = B200AUG_S_EMPTY_BOX;
     P.rs_mode = RS_COPY;
@@ -375,7 +392,24 @@ __device__ void plan_resize(const B200AugFusedArgs& a, const PlanCore& c, Plan& 
     double scale_factor = 0.5 * ((double)ow / (double)c.cw + (double)oh / (double)c.ch);
     P.scale_x = 1.0 / ((double)ow / (double)c.cw);
     P.scale_y = 1.0 / ((double)oh / (double)c.ch);
-    if (scale_factor < 1.0) {
+    if (scale_factor < 1.0 && a.downfilter != B200AUG_DOWN_AREA && (a.flags & B200AUG_F_FOCUS)) {
+      // _resize with downfilter gaussian / hamming (image_geometric_cv2.py:47-62,76-81): smooth at canvas resolution, then
+      // INTER_LINEAR.  Tap counts: cv2.GaussianBlur's cvRound(sigma * 3 * 2 + 1) | 1 for 8-bit images, sigma = 0.5 / scale;
+      // the Hamming window's round(2 / scale + 1) made odd.
+      int n;
+      if (a.downfilter == B200AUG_DOWN_GAUSSIAN) {
+        n = gaussian_ksize_u8(0.5 / scale_factor);  // (the row kernel; the column kernel has 7 taps, see prefilter_kernel)
+      } else {
+        const double ks = 1.0 / scale_factor;
+        n = max(1, rint_d2i(ks * 2.0 + 1.0));
+        n |= 1;
+      }
+      P.rs_mode = RS_LINEAR;
+      P.prefilter = a.downfilter;
+      P.pf_n = n;
+      P.pf_sf = scale_factor;
+      if (n > B200AUG_PREFILTER_MAX_TAPS) P.status = B200AUG_S_UNSUPPORTED;
+    } else if (scale_factor < 1.0) {
       if (P.scale_x >= 1.0 && P.scale_y >= 1.0) {
         P.iscale_x = rint_d2i(P.scale_x);
         P.iscale_y = rint_d2i(P.scale_y);
@@ -1347,7 +1381,19 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
   if (tid == 0) {
     // rotated samples: the canvas goes to this sample's workspace region (if it fits), the canvas workers fill it
     bool canvas = false;
-    if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.status == B200AUG_S_OK && P.cw <= DT_CAP && P.ch <= DT_CAP) {
+    if (P.prefilter && with_tables) {
+      // prefiltered samples: prefilter_kernel produces the (cropped or warped) canvas itself and leaves it smoothed in the
+      // workspace; without room for it the sample cannot be served
+      const int spitch = canvas_pitch(P.cw);
+      if (P.status == B200AUG_S_OK) {
+        if (with_tables && a.plans && a.workspace && (int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
+          P.cv_ptr = a.workspace + (size_t)b * a.workspace_stride;
+          P.cv_pitch = spitch;
+        } else {
+          P.status = B200AUG_S_UNSUPPORTED;
+        }
+      }
+    } else if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.status == B200AUG_S_OK && P.cw <= DT_CAP && P.ch <= DT_CAP) {
       const int spitch = canvas_pitch(P.cw);
       if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
         P.cv_ptr = a.workspace + (size_t)b * a.workspace_stride;
@@ -1381,6 +1427,140 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
       const uint4* src = reinterpret_cast<const uint4*>(smem);
       for (int i = tid; i < nvec; i += NTHREADS) dst[i] = src[i];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ anti-alias prefilters
+
+// _apply_antialias_filter (image_geometric_cv2.py:47-62) for the samples plan_kernel marked (Plan::prefilter): the canvas --
+// the zero-padded crop, or the cv2.warpAffine image of a rotated sample -- smoothed at its own resolution into the sample's
+// workspace region; the fused kernel then resizes it with cv2's INTER_LINEAR (:76-81) like any crop.
+//   gaussian: the reference writes cv2.GaussianBlur(img, (0, 0), ks, ks, cv2.BORDER_REPLICATE) with ks = 0.5 / scale, and
+//     Python binds that as sigmaX = ks, dst = ks (ignored), sigmaY = BORDER_REPLICATE = 1.0, default border: a
+//     cvRound(6 ks + 1) | 1 tap kernel along rows, 7 taps (sigma 1) along columns, BORDER_REFLECT_101.  That is what is
+//     reproduced here (oracle/cv2_model.py:REFERENCE_GAUSSIAN_SIGMA_Y).  On 8-bit images the blur is exact integer work:
+//     8-bit fixed point taps (error-diffused so that they sum to 256), rows then columns, (sum + 2^15) >> 16
+//     (oracle/cv2_model.py:gaussian_kernel_fixed, gaussian_blur_u8);
+//   hamming:  cv2.sepFilter2D(img, -1, k, k), BORDER_REFLECT_101, float32: rows s = k0 p0, s = fma(ki, pi, s); columns the
+//     same, or for a kernel cv2 classifies as symmetric s = kc hc, s = fma(k[c+i], h[c-i] + h[c+i], s); rint, saturate
+//     (oracle/cv2_model.py:sep_filter_u8 -- the arithmetic of cv2's vector loops).  The window comes from the caller's table
+//     (B200AugFusedArgs::hamming_taps): whether cv2 sees it as symmetric hangs on the last bit of the host's cos().
+// A non-default configuration (the samplers always ask for area / linear, geometric.py:76-77), so this is a plain tiled
+// kernel: PF_CTAS CTAs per sample walk its 32 x 32 canvas tiles -- stage tile + halo through canvas_px() with the border
+// rule applied to the canvas coordinates, horizontal pass into shared memory, vertical pass, store.
+constexpr int PF_TILE = 32;
+constexpr int PF_CTAS = 8;  // CTAs per sample
+constexpr int PF_MAXR = B200AUG_PREFILTER_MAX_TAPS / 2;
+constexpr int PF_SIDE = PF_TILE + 2 * PF_MAXR;  // 94: staged rows / columns at the widest kernel
+constexpr double PF_GAUSS_SIGMA_Y = 1.0;        // (see above)
+
+__device__ __forceinline__ int border_reflect101(int p, int len) {  // cv::borderInterpolate(BORDER_REFLECT_101)
+  if ((unsigned)p < (unsigned)len) return p;
+  if (len == 1) return 0;
+  do {
+    if (p < 0) p = -p;
+    else p = 2 * len - p - 2;
+  } while ((unsigned)p >= (unsigned)len);
+  return p;
+}
+
+// the n fixed-point taps (bit patterns of int32) of cv2's 8-bit Gaussian; one thread
+__device__ void gaussian_taps_fixed(double sigma, int n, float* ktab) {
+  const int r = n >> 1;
+  const double s2 = -0.5 / (sigma * sigma);
+  double vals[PF_MAXR + 1], sum = 0.0;
+  for (int i = 0; i < r; ++i) {
+    const double x = (double)(i - r);
+    vals[i] = exp(s2 * x * x);
+    sum += vals[i];
+  }
+  const double norm = 1.0 / (2.0 * sum + 1.0);
+  double err = 0.0;
+  int tot = 0;
+  for (int i = 0; i < r; ++i) {
+    const double adj = vals[i] * norm * 256.0 + err;
+    const int v0 = rint_d2i(adj);
+    err = adj - (double)v0;
+    ktab[i] = __int_as_float(v0);
+    ktab[n - 1 - i] = __int_as_float(v0);
+    tot += v0;
+  }
+  ktab[r] = __int_as_float(256 - 2 * tot);
+}
+
+__global__ void __launch_bounds__(NTHREADS) prefilter_kernel(const __grid_constant__ KArgs K) {
+  const B200AugFusedArgs& a = K.a;
+  __shared__ __align__(16) unsigned char plan_raw[(sizeof(Plan) + 15) & ~size_t(15)];
+  __shared__ uint8_t staged[PF_SIDE][PF_SIDE + 2];
+  __shared__ float hbuf[PF_SIDE][PF_TILE + 1];  // gaussian: int32 bit patterns
+  __shared__ float ktx[B200AUG_PREFILTER_MAX_TAPS + 1], kty[B200AUG_PREFILTER_MAX_TAPS + 1];  // gaussian: int32 bit patterns
+  const int b = blockIdx.x / PF_CTAS, part = blockIdx.x % PF_CTAS, tid = threadIdx.x;
+  {
+    const uint4* rec = reinterpret_cast<const uint4*>(a.plans + (size_t)b * a.plan_stride);
+    uint4* dst = reinterpret_cast<uint4*>(plan_raw);
+    for (int i = tid; i < (int)(plan_bytes() >> 4); i += NTHREADS) dst[i] = rec[i];
+  }
+  __syncthreads();
+  const Plan& P = *reinterpret_cast<const Plan*>(plan_raw);
+  if (!P.prefilter || P.status != B200AUG_S_OK || P.cv_ptr == nullptr) return;
+  const bool gauss = P.prefilter == B200AUG_DOWN_GAUSSIAN;
+  const int nx = P.pf_n, ny = gauss ? gaussian_ksize_u8(PF_GAUSS_SIGMA_Y) : nx;
+  const int rx = nx >> 1, ry = ny >> 1, cw = P.cw, ch = P.ch;
+  bool sym = false;
+  if (gauss) {
+    if (tid == 0) gaussian_taps_fixed(0.5 / P.pf_sf, nx, ktx);
+    if (tid == 32) gaussian_taps_fixed(PF_GAUSS_SIGMA_Y, ny, kty);
+  } else {
+    if (tid < nx) ktx[tid] = kty[tid] = a.hamming_taps[(size_t)rx * 64 + tid];
+    sym = (a.hamming_sym_mask >> rx) & 1ull;
+  }
+  __syncthreads();
+  const int side_x = PF_TILE + 2 * rx, side_y = PF_TILE + 2 * ry;
+  const int ntx = (cw + PF_TILE - 1) / PF_TILE, nty = (ch + PF_TILE - 1) / PF_TILE;
+  for (int t = part; t < ntx * nty; t += PF_CTAS) {
+    const int tx0 = (t % ntx) * PF_TILE, ty0 = (t / ntx) * PF_TILE;
+    // ---- stage tile + halo (canvas coordinates folded back into the canvas by the border rule)
+    for (int i = tid; i < side_x * side_y; i += NTHREADS) {
+      const int yy = i / side_x, xx = i - yy * side_x;
+      staged[yy][xx] = (uint8_t)canvas_px(P, border_reflect101(tx0 - rx + xx, cw), border_reflect101(ty0 - ry + yy, ch));
+    }
+    __syncthreads();
+    // ---- rows
+    for (int i = tid; i < side_y * PF_TILE; i += NTHREADS) {
+      const int yy = i / PF_TILE, x = i % PF_TILE;
+      if (gauss) {
+        int sacc = 0;
+        for (int k = 0; k < nx; ++k) sacc += __float_as_int(ktx[k]) * (int)staged[yy][x + k];
+        hbuf[yy][x] = __int_as_float(sacc);
+      } else {
+        float sacc = __fmul_rn(ktx[0], (float)staged[yy][x]);
+        for (int k = 1; k < nx; ++k) sacc = __fmaf_rn(ktx[k], (float)staged[yy][x + k], sacc);
+        hbuf[yy][x] = sacc;
+      }
+    }
+    __syncthreads();
+    // ---- columns
+    for (int i = tid; i < PF_TILE * PF_TILE; i += NTHREADS) {
+      const int y = i / PF_TILE, x = i % PF_TILE;
+      int q;
+      if (gauss) {
+        int sacc = 0;
+        for (int k = 0; k < ny; ++k) sacc += __float_as_int(kty[k]) * __float_as_int(hbuf[y + k][x]);
+        q = (sacc + (1 << 15)) >> 16;
+      } else {
+        float sacc;
+        if (sym) {
+          sacc = __fmul_rn(kty[ry], hbuf[y + ry][x]);
+          for (int k = 1; k <= ry; ++k) sacc = __fmaf_rn(kty[ry + k], __fadd_rn(hbuf[y + ry - k][x], hbuf[y + ry + k][x]), sacc);
+        } else {
+          sacc = __fmul_rn(kty[0], hbuf[y][x]);
+          for (int k = 1; k < ny; ++k) sacc = __fmaf_rn(kty[k], hbuf[y + k][x], sacc);
+        }
+        q = __float2int_rn(sacc);
+      }
+      if (tx0 + x < cw && ty0 + y < ch) P.cv_ptr[(size_t)(ty0 + y) * P.cv_pitch + tx0 + x] = (uint8_t)min(max(q, 0), 255);
+    }
+    __syncthreads();
   }
 }
 
@@ -1812,8 +1992,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
   }
   // ---- rotated samples: the canvas workers leave the cv2.warpAffine canvas in the workspace; from here on the sample is a
   // plain crop of it (image_geometric_cv2.py:121-134: warpAffine at source resolution, then cv2.resize)
-  if (P.src_mode == SRC_WARP && P.cv_ptr != nullptr) {
-    if (tid == 0) {
+  // (prefiltered samples: prefilter_kernel, ahead of this kernel in the stream, left the smoothed canvas there)
+  if ((P.src_mode == SRC_WARP || P.prefilter) && P.cv_ptr != nullptr) {
+    if (tid == 0 && !P.prefilter) {
       const uint32_t* done = plan_tail(a.plans, a.batch, a.plan_stride).done + b;
       uint32_t v;
       for (;;) {
@@ -2532,6 +2713,23 @@ extern "C" int64_t b200aug_workspace_stride(int max_side) {
   return ((spitch * (max_side + 1)) + 255) & ~int64_t(255);
 }
 
+extern "C" int b200aug_hamming_table(const double* windows, float* taps_out, uint64_t* sym_mask_out) {
+  if (!windows || !taps_out || !sym_mask_out) return B200AUG_E_INVALID_ARG;
+  uint64_t mask = 0;
+  for (int r = 0; r < 32; ++r) {
+    const int n = 2 * r + 1;
+    bool sym = true;
+    for (int i = 0; i < 64; ++i) {
+      const double v = (r > 0 && i < n) ? windows[r * 64 + i] : 0.0;
+      taps_out[r * 64 + i] = (float)v;
+      if (r > 0 && i < n && v != windows[r * 64 + (n - 1 - i)]) sym = false;  // cv::getKernelType: exact mirror equality
+    }
+    if (sym && r > 0) mask |= 1ull << r;
+  }
+  *sym_mask_out = mask;
+  return B200AUG_OK;
+}
+
 extern "C" int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
                                         int32_t batch, const int32_t* row_lo, const int32_t* row_hi, void* stream) {
   if (!dev_frames || !host_frames || frame_stride <= 0 || pitch <= 0 || batch < 0 || !row_lo || !row_hi) return B200AUG_E_INVALID_ARG;
@@ -2643,6 +2841,11 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
       w = (a.warp_ctas > 0) ? a.warp_ctas : (3 * n_sm) / 2;
     K.a.warp_ctas = (w + cl - 1) / cl * cl;
   }
+  // anti-alias prefilters keep their smoothed canvases in the workspace and are planned by plan_kernel
+  const bool prefilter = want_image && (a.flags & B200AUG_F_FOCUS) && a.downfilter != B200AUG_DOWN_AREA;
+  if (a.downfilter < B200AUG_DOWN_AREA || a.downfilter > B200AUG_DOWN_HAMMING) return B200AUG_E_INVALID_ARG;
+  if (prefilter && a.downfilter == B200AUG_DOWN_HAMMING && !a.hamming_taps) return B200AUG_E_INVALID_ARG;
+  if (prefilter && (!records || !a.workspace)) return B200AUG_E_UNSUPPORTED;
   if (a.phase < B200AUG_PHASE_ALL || a.phase > B200AUG_PHASE_MAIN) return B200AUG_E_INVALID_ARG;
   if (a.phase == B200AUG_PHASE_MAIN && !records) return B200AUG_E_INVALID_ARG;  // nothing to pick the plans up from
   if (a.phase != B200AUG_PHASE_MAIN) {
@@ -2669,7 +2872,13 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
     attr_smem = (int)smem;
   }
 
-  const int dep_mode = (records && a.phase == B200AUG_PHASE_ALL) ? 1 : 0;  // (MAIN alone: plain stream / event order)
+  if (prefilter) {  // (a no-op for samples whose plan asks for no prefilter: those that do not down-scale)
+    prefilter_kernel<<<a.batch * PF_CTAS, NTHREADS, 0, st>>>(K);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e);
+  }
+  // (MAIN alone, or behind prefilter_kernel: plain stream / event order)
+  const int dep_mode = (records && a.phase == B200AUG_PHASE_ALL && !prefilter) ? 1 : 0;
   cudaLaunchAttribute pdl;
   pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   pdl.val.programmaticStreamSerializationAllowed = 1;

@@ -8,12 +8,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200AUG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libb200aug.so")  # (env: experiment builds)
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_FIELDS, NUM_OPS, NUM_NOISE = 8, 6, 4
 
 F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETRIC, F_WHITEN, F_INSERT_BACKTRANSFORM = 1, 2, 4, 8, 16, 32, 64, 128
 CAT_GENERAL, CAT_QUAT, CAT_XYS, CAT_ROI, CAT_POINTS, CAT_BACKTRANSFORM = 0, 1, 2, 3, 4, 5
 PHASE_ALL, PHASE_PLAN, PHASE_MAIN = 0, 1, 2
+DOWN_AREA, DOWN_GAUSSIAN, DOWN_HAMMING = 0, 1, 2
+PREFILTER_MAX_TAPS = 63
 S_OK, S_EMPTY_BOX, S_UNSUPPORTED, S_ROWBUF = 0, 1, 2, 3
 OP_EQUALIZE, OP_POSTERIZE, OP_GAMMA, OP_CONTRAST, OP_BRIGHTNESS, OP_BLUR = range(6)
 
@@ -46,11 +48,12 @@ class FusedArgs(C.Structure):
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),
                 ("trace_out", C.c_void_p), ("order", C.c_void_p), ("workspace", C.c_void_p), ("workspace_stride", C.c_int64),
                 ("plans", C.c_void_p), ("plan_stride", C.c_int64), ("warp_ctas", C.c_int32), ("phase", C.c_int32),
+                ("downfilter", C.c_int32), ("reserved0", C.c_int32), ("hamming_taps", C.c_void_p), ("hamming_sym_mask", C.c_uint64),
                 ("photo", PhotoParams)]
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
+           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_hamming_table", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
            "b200aug_quat_matrix", "b200aug_jpeg_info", "b200aug_decode_jpeg_gray", "b200aug_jpeg_last_status", "b200aug_jpeg_backend")
 
 
@@ -95,6 +98,8 @@ def _load():
     lib.b200aug_decode_jpeg_gray.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200aug_jpeg_last_status.restype = C.c_int
     lib.b200aug_jpeg_backend.restype = C.c_int
+    lib.b200aug_hamming_table.restype = C.c_int
+    lib.b200aug_hamming_table.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     if lib.b200aug_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {lib.b200aug_abi_version()} vs binding {ABI_VERSION}")
     return lib

@@ -24,7 +24,8 @@ _CAT_CODE = {
 }
 _CAT_DIMS = {N.CAT_QUAT: (4,), N.CAT_XYS: (3,), N.CAT_ROI: (4,), N.CAT_POINTS: (2, 3)}
 
-STATUS_TEXT = {N.S_EMPTY_BOX: "empty view box", N.S_UNSUPPORTED: "unsupported resampler (INTER_AREA with one axis up-scaling)",
+STATUS_TEXT = {N.S_EMPTY_BOX: "empty view box",
+               N.S_UNSUPPORTED: f"anti-alias prefilter wider than {N.PREFILTER_MAX_TAPS} taps, or its canvas exceeds the workspace",
                N.S_ROWBUF: "source segment exceeds rowbuf_capacity"}
 
 
@@ -258,6 +259,52 @@ def _workspace(device, B: int):
 
 _PLAN_BUFFERS: Dict[Any, torch.Tensor] = {}
 
+DOWNFILTER_CODES = {None: N.DOWN_AREA, "area": N.DOWN_AREA, "gaussian": N.DOWN_GAUSSIAN, "hamming": N.DOWN_HAMMING}
+_HAMMING_TABLES: Dict[Any, Tuple[torch.Tensor, int]] = {}
+
+
+def hamming_windows() -> np.ndarray:
+    """float64 [32, 64]: row r holds the normalised Hamming window of 2 r + 1 taps, evaluated the way the reference's
+    scipy.signal.windows.hamming does (image_geometric_cv2.py:51-57: general cosine sum over linspace(-pi, pi, n) with the
+    coefficients [0.54, 1 - 0.54], then divided by its sum) -- the last bit matters: cv2 picks its column filter by whether
+    the float64 window is exactly mirror symmetric."""
+    out = np.zeros((32, 64), np.float64)
+    coeff = (0.54, 1.0 - 0.54)
+    for r in range(1, 32):
+        n = 2 * r + 1
+        fac = np.linspace(-np.pi, np.pi, n)
+        w = np.zeros(n)
+        for k, a in enumerate(coeff):
+            w += a * np.cos(k * fac)
+        out[r, :n] = w / np.sum(w)
+    return out
+
+
+def hamming_table(device) -> Tuple[torch.Tensor, int]:
+    """Device copy of the window table + cv2's symmetry bits (B200AugFusedArgs.hamming_taps / hamming_sym_mask), cached."""
+    key = (device.type, device.index)
+    hit = _HAMMING_TABLES.get(key)
+    if hit is None:
+        win = np.ascontiguousarray(hamming_windows())
+        taps = np.zeros(32 * 64, np.float32)
+        mask = C.c_uint64(0)
+        N.check(N.lib.b200aug_hamming_table(win.ctypes.data, taps.ctypes.data, C.byref(mask)), "b200aug_hamming_table")
+        hit = (torch.from_numpy(taps).to(device), int(mask.value))
+        _HAMMING_TABLES[key] = hit
+    return hit
+
+
+def set_downfilter(args, downfilter: Optional[str], device) -> List[Any]:
+    """Fill B200AugFusedArgs.downfilter (+ the Hamming table); returns what must outlive the launch."""
+    if downfilter not in DOWNFILTER_CODES:
+        raise ValueError(f"downfilter {downfilter!r}: one of 'area', 'gaussian', 'hamming'")
+    args.downfilter = DOWNFILTER_CODES[downfilter]
+    if args.downfilter == N.DOWN_HAMMING:
+        taps, mask = hamming_table(device)
+        args.hamming_taps, args.hamming_sym_mask = taps.data_ptr(), mask
+        return [taps]
+    return []
+
 
 def _plan_buffer(device, B: int, ow: int, oh: int):
     """Scratch for the plans + resize tables of one launch (B200AugFusedArgs.plans), cached like the canvas workspace."""
@@ -353,7 +400,8 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   beyond_border_shift: float = 0.3, insert_backtransform: bool = False, rowbuf_capacity: int = 0,
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
                   want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0,
-                  schedule: bool = True, preplan: bool = True, private_scratch: bool = False) -> PreparedCall:
+                  schedule: bool = True, preplan: bool = True, private_scratch: bool = False,
+                  downfilter: Optional[str] = None) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -380,6 +428,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     args.warp_ctas = int(os.environ.get("B200AUG_WARP_CTAS", "0"))  # experiment knob, 0 = library default
     keep: List[Any] = []
     out_data: Dict[str, Any] = {}
+    keep += set_downfilter(args, downfilter, device)
 
     # ---- fields
     image_keys = [k for k in batch.keys() if as_category(meta.categories.get(k)) == FieldCategory.image]

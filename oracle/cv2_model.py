@@ -186,3 +186,162 @@ def resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     r1 = np.clip(yo + 1, 0, sh - 1)
     out = (((b0[:, None] * (H[r0] >> 4)) >> 16) + ((b1[:, None] * (H[r1] >> 4)) >> 16) + 2) >> 2
     return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------- anti-alias prefilters
+# trackertraincode/datatransformation/tensors/image_geometric_cv2.py:47-62 (_apply_antialias_filter): the image is smoothed
+# at its own resolution and then resized with INTER_LINEAR (:76-81).
+
+GAUSS_FRACTION_BITS = 8  # cv2.GaussianBlur on u8: taps as 8.8 fixed point (ufixedpoint16), exact integer arithmetic
+
+
+def gaussian_ksize_u8(sigma: float) -> int:
+    """Kernel size cv2.GaussianBlur derives from sigma for 8-bit images when ksize = (0, 0): cvRound(sigma*3*2 + 1) | 1."""
+    return int(np.rint(sigma * 3 * 2 + 1)) | 1
+
+
+def gaussian_kernel_fixed(sigma: float) -> np.ndarray:
+    """The 8-bit fixed-point Gaussian taps of cv2.GaussianBlur(u8): exp(-x^2 / (2 sigma^2)) normalised in double, scaled by
+    256 and rounded with the rounding error carried to the next tap ("error diffusion", both halves mirrored); the centre
+    tap takes whatever makes the sum exactly 256.  int64[n]."""
+    n = gaussian_ksize_u8(sigma)
+    n2 = (n - 1) // 2
+    x = np.arange(n2, dtype=np.float64) - n2
+    vals = np.exp((-0.5 / (sigma * sigma)) * x * x)
+    norm = 1.0 / (2.0 * vals.sum() + 1.0)
+    out = np.zeros(n, np.int64)
+    err, tot = 0.0, 0
+    for i in range(n2):
+        adj = vals[i] * norm * float(1 << GAUSS_FRACTION_BITS) + err
+        v0 = int(np.rint(adj))
+        err = adj - v0
+        out[i] = out[n - 1 - i] = v0
+        tot += v0
+    out[n2] = (1 << GAUSS_FRACTION_BITS) - 2 * tot
+    return out
+
+
+def reflect101(idx, size: int) -> np.ndarray:
+    """cv::borderInterpolate(BORDER_REFLECT_101) on an index array (folds repeatedly when the overhang exceeds the size)."""
+    idx = np.asarray(idx).copy()
+    if size == 1:
+        return np.zeros_like(idx)
+    while True:
+        bad = (idx < 0) | (idx >= size)
+        if not bad.any():
+            return idx
+        idx = np.where(idx < 0, -idx, idx)
+        idx = np.where(idx >= size, 2 * size - idx - 2, idx)
+
+
+def _border_index(idx, size: int, border: str) -> np.ndarray:
+    return np.clip(idx, 0, size - 1) if border == "replicate" else reflect101(idx, size)
+
+
+def gaussian_blur_u8(src: np.ndarray, sigma_x: float, sigma_y: float = None, border: str = "reflect101") -> np.ndarray:
+    """cv2.GaussianBlur(src, (0, 0), sigmaX=sigma_x, sigmaY=sigma_y, borderType=REFLECT_101 | REPLICATE), u8 1-channel:
+    rows (sigma_x taps) then columns (sigma_y taps) in integers, (sum + 2^15) >> 16 at the end."""
+    assert src.dtype == np.uint8 and src.ndim == 2
+    kx = gaussian_kernel_fixed(sigma_x)
+    ky = gaussian_kernel_fixed(sigma_x if sigma_y is None else sigma_y)
+    h, w = src.shape
+    S = src.astype(np.int64)
+    hp = sum(kx[i] * S[:, _border_index(np.arange(w) + i - len(kx) // 2, w, border)] for i in range(len(kx)))
+    v = sum(ky[i] * hp[_border_index(np.arange(h) + i - len(ky) // 2, h, border)] for i in range(len(ky)))
+    return np.clip((v + (1 << 15)) >> 16, 0, 255).astype(np.uint8)
+
+
+# What the reference's gaussian down-filter really computes.  image_geometric_cv2.py:50 calls
+#   cv2.GaussianBlur(img, (0, 0), ks, ks, cv2.BORDER_REPLICATE)
+# positionally, and the Python signature is GaussianBlur(src, ksize, sigmaX[, dst[, sigmaY[, borderType]]]): the second `ks`
+# lands in `dst` (ignored) and BORDER_REPLICATE (= 1) in sigmaY.  So: sigmaX = 0.5 / scale, sigmaY = 1.0 (7 taps), default
+# border (REFLECT_101).  Results "identical to the reference's" means reproducing exactly that.
+REFERENCE_GAUSSIAN_SIGMA_Y = 1.0
+REFERENCE_GAUSSIAN_BORDER = "reflect101"
+
+
+def hamming_kernel(scale_factor: float) -> np.ndarray:
+    """The normalised Hamming window of image_geometric_cv2.py:51-57 (float64[n], n odd >= 3 for scale_factor < 1):
+    scipy.signal.windows.hamming(n) = 0.54 - 0.46 cos(2 pi i / (n - 1)), evaluated the way scipy does
+    (0.54 + 0.46 cos(linspace(-pi, pi, n))) because the last bit decides whether cv2 sees a symmetric kernel."""
+    ks = 1.0 / scale_factor
+    n = max(1, round(ks * 2 + 1))
+    n = n if (n & 1) else n + 1
+    if n == 1:
+        return np.ones(1)
+    fac = np.linspace(-np.pi, np.pi, n)
+    w = np.zeros(n)
+    for k, a in enumerate((0.54, 1.0 - 0.54)):  # (general_hamming passes [alpha, 1 - alpha])
+        w += a * np.cos(k * fac)
+    return w / np.sum(w)
+
+
+def _fma32(a, b, c):
+    """float32 fused multiply-add of arrays, exactly rounded: the product of two float32 is exact in float64, the sum is
+    rounded once to 53 bits and once more to 24 -- the rare double-rounding cases (the float64 sum sits exactly on a float32
+    rounding boundary) are redone in rational arithmetic."""
+    from fractions import Fraction
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    c = np.asarray(c, np.float32)
+    a, b, c = np.broadcast_arrays(a, b, c)
+    s = a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)
+    out = s.astype(np.float32)
+    risky = (s.view(np.uint64) & np.uint64((1 << 29) - 1)) == np.uint64(1 << 28)
+    if risky.any():
+        out = out.copy()
+        for idx in zip(*np.nonzero(risky)):
+            exact = Fraction(float(a[idx])) * Fraction(float(b[idx])) + Fraction(float(c[idx]))
+            lo = np.float32(s[idx])
+            cands = [lo, np.nextafter(lo, np.float32(np.inf)), np.nextafter(lo, np.float32(-np.inf))]
+            # nearest float32; ties to even mantissa
+            best = min(cands, key=lambda f: (abs(Fraction(float(f)) - exact), int(np.float32(f).view(np.uint32)) & 1))
+            out[idx] = best
+    return out
+
+
+def sep_filter_symmetric_flag(k: np.ndarray) -> bool:
+    """cv::getKernelType's KERNEL_SYMMETRICAL test: exact mirror equality of the double coefficients."""
+    return bool(np.array_equal(k, k[::-1]))
+
+
+def sep_filter_u8(src: np.ndarray, k: np.ndarray) -> np.ndarray:
+    """cv2.sepFilter2D(src, -1, k, k) for a u8 1-channel image and a float64 kernel that cv2 does not classify as a
+    symmetric smoothing kernel in integers -- i.e. its float32 path (filter.simd.hpp), border BORDER_REFLECT_101:
+      rows:    s = k[0] p[0];  s = fma(k[i], p[i], s)                                   i = 1 .. n-1
+      columns: symmetric k:   s = k[c] h[c];  s = fma(k[c+i], h[c-i] + h[c+i], s)       i = 1 .. c
+               otherwise:     s = k[0] h[0];  s = fma(k[i], h[i], s)
+      out = saturate_u8(rint(s)).
+    This is the arithmetic of cv2's vector loops (AVX2 / AVX-512 builds); the last `width mod V` columns of an image go
+    through cv2's scalar tail loops, which round differently (V depends on the CPU), so against the live binary the model is
+    bit-exact on the vector body and within 1 LSB on a handful of tail pixels (tests/test_oracle_cv2_model.py)."""
+    assert src.dtype == np.uint8 and src.ndim == 2
+    kf = np.asarray(k, np.float64).astype(np.float32)
+    n, c = len(kf), len(kf) // 2
+    h, w = src.shape
+
+    S = src.astype(np.float32)
+    cols = [reflect101(np.arange(w) + i - c, w) for i in range(n)]
+    hp = kf[0] * S[:, cols[0]]
+    for i in range(1, n):
+        hp = _fma32(kf[i], S[:, cols[i]], hp)
+    rows = [reflect101(np.arange(h) + i - c, h) for i in range(n)]
+    if sep_filter_symmetric_flag(np.asarray(k, np.float64)):
+        v = kf[c] * hp[rows[c]]
+        for i in range(1, c + 1):
+            v = _fma32(kf[c + i], hp[rows[c - i]] + hp[rows[c + i]], v)
+    else:
+        v = kf[0] * hp[rows[0]]
+        for i in range(1, n):
+            v = _fma32(kf[i], hp[rows[i]], v)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def antialias_prefilter_u8(img: np.ndarray, scale_factor: float, kind: str) -> np.ndarray:
+    """_apply_antialias_filter (image_geometric_cv2.py:47-62) for u8 1-channel images -- as the reference's calls evaluate
+    (see REFERENCE_GAUSSIAN_SIGMA_Y above)."""
+    if kind == "gaussian":
+        return gaussian_blur_u8(img, 0.5 / scale_factor, REFERENCE_GAUSSIAN_SIGMA_Y, REFERENCE_GAUSSIAN_BORDER)
+    if kind == "hamming":
+        return sep_filter_u8(img, hamming_kernel(scale_factor))
+    raise NotImplementedError(kind)

@@ -97,11 +97,31 @@ def extract_roi_zero_padded(img: np.ndarray, roi) -> np.ndarray:
     return out
 
 
-def resize_area_or_linear(img: np.ndarray, new_w: int, new_h: int, use_model=False) -> np.ndarray:
-    """_resize (image_geometric_cv2.py:65-82) with downfilter='area', upfilter='linear' (the sampler's fixed choice,
-    geometric.py:76-77): INTER_AREA when the mean scale < 1 else INTER_LINEAR."""
+def antialias_prefilter(img: np.ndarray, scale_factor: float, kind: str, use_model=False) -> np.ndarray:
+    """_apply_antialias_filter (image_geometric_cv2.py:47-62): the cv2 calls, or their models."""
+    if use_model:
+        return cv2_model.antialias_prefilter_u8(img, scale_factor, kind)
+    if kind == "gaussian":
+        # the reference's call as Python binds it: sigmaX = ks, sigmaY = 1.0, default border (cv2_model.py explains)
+        ks = 0.5 / scale_factor
+        return cv2.GaussianBlur(img, (0, 0), sigmaX=ks, sigmaY=cv2_model.REFERENCE_GAUSSIAN_SIGMA_Y, borderType=cv2.BORDER_REFLECT_101)
+    if kind == "hamming":
+        kern = cv2_model.hamming_kernel(scale_factor)
+        return cv2.sepFilter2D(img, -1, kern, kern)
+    raise NotImplementedError(f"Filter: {kind}")
+
+
+def resize_area_or_linear(img: np.ndarray, new_w: int, new_h: int, use_model=False, downfilter="area") -> np.ndarray:
+    """_resize (image_geometric_cv2.py:65-82) with upfilter='linear': when the mean scale is < 1, INTER_AREA
+    (downfilter='area', the sampler's fixed choice, geometric.py:76-77) or the gaussian / hamming prefilter followed by
+    INTER_LINEAR; INTER_LINEAR otherwise."""
     old_h, old_w = img.shape[:2]
     scale_factor = 0.5 * (new_w / old_w + new_h / old_h)
+    if scale_factor < 1.0 and downfilter in ("gaussian", "hamming"):
+        img = antialias_prefilter(img, scale_factor, downfilter, use_model)
+        if use_model:
+            return cv2_model.resize_linear_u8(img, new_w, new_h)
+        return cv2.resize(img, dsize=(new_w, new_h), interpolation=cv2.INTER_LINEAR)
     area = scale_factor < 1.0
     if use_model:
         fn = cv2_model.resize_area_u8 if area else cv2_model.resize_linear_u8
@@ -109,10 +129,10 @@ def resize_area_or_linear(img: np.ndarray, new_w: int, new_h: int, use_model=Fal
     return cv2.resize(img, dsize=(new_w, new_h), interpolation=cv2.INTER_AREA if area else cv2.INTER_LINEAR)
 
 
-def croprescale_image(img: np.ndarray, roi, new_wh, use_model=False) -> np.ndarray:
+def croprescale_image(img: np.ndarray, roi, new_wh, use_model=False, downfilter="area") -> np.ndarray:
     """croprescale_image_cv2 (image_geometric_cv2.py:138-155), [H, W] u8 in, [oh, ow] u8 out."""
     ow, oh = new_wh
-    return resize_area_or_linear(extract_roi_zero_padded(img, roi), ow, oh, use_model)
+    return resize_area_or_linear(extract_roi_zero_padded(img, roi), ow, oh, use_model, downfilter)
 
 
 def warp_plan(tr, new_wh):
@@ -132,7 +152,7 @@ def warp_plan(tr, new_wh):
     return M, rot_w, rot_h, False
 
 
-def affine_transform_image(img: np.ndarray, tr, new_wh, use_model=False) -> np.ndarray:
+def affine_transform_image(img: np.ndarray, tr, new_wh, use_model=False, downfilter="area") -> np.ndarray:
     """affine_transform_image_cv2: anti-aliased warpAffine = warp to an intermediate canvas, then area-resize."""
     ow, oh = new_wh
     M, cw, ch, up = warp_plan(tr, new_wh)
@@ -142,14 +162,14 @@ def affine_transform_image(img: np.ndarray, tr, new_wh, use_model=False) -> np.n
         canvas = cv2.warpAffine(img, M=M, dsize=(cw, ch), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=None)
     if up:
         return canvas
-    return resize_area_or_linear(canvas, ow, oh, use_model)
+    return resize_area_or_linear(canvas, ow, oh, use_model, downfilter)
 
 
 # ----------------------------------------------------------------------------- sample-level transforms
 
 
 def focus_roi(sample: Sample, params: RoiFocusParams, new_size, roi_variable="roi", insert_backtransform=False,
-              beyond_border_shift=0.3, use_model=False) -> Tuple[Sample, dict]:
+              beyond_border_shift=0.3, use_model=False, downfilter="area") -> Tuple[Sample, dict]:
     """GeneralFocusRoi.__call__ (geometric.py:193-231) with explicit parameters.
 
     Returns the transformed sample and the intermediates the parity tests compare bit-exactly
@@ -166,9 +186,9 @@ def focus_roi(sample: Sample, params: RoiFocusParams, new_size, roi_variable="ro
         if c == CAT_IMAGE:
             img = v[..., 0] if v.ndim == 3 else v
             if F32(params.angle) != 0.0:
-                res = affine_transform_image(img, tr, new_wh, use_model)
+                res = affine_transform_image(img, tr, new_wh, use_model, downfilter)
             else:
-                res = croprescale_image(img, view_i, new_wh, use_model)
+                res = croprescale_image(img, view_i, new_wh, use_model, downfilter)
             out.data[k] = res[None, ...]
         elif c in IMAGELIKE:
             raise NotImplementedError("semseg fields are outside the hot path")
