@@ -281,6 +281,17 @@ int b200aug_corrected_rotation(const float* half_sizes, int64_t size_stride, flo
                                const float* coord, int64_t coord_stride, const float* pose, float* out, float* look_at_out,
                                int batch, void* stream);
 
+/* PutRoiFromLandmarks(extend_to_forehead=True) (batch/misc.py:14-26): roi_out[b] = [min_x, min_y, max_x, max_y] over all
+ * vertices of the posed deformable face model (PosedDeformableHead, neuralnets/modelcomponents.py:38-56,85-94):
+ *   (quat[b] rotates (vertices + sum_k deform_base[k] * shapeparams[b][k])) * coord[b][2] + (coord[b][0:2] + xy_offset).
+ * vertices [V,3] and deform_base [K,V,3] (K <= 64) are the scaled BFM arrays of facemodel/bfm.py:49-72, device memory;
+ * shapeparams [B,K] may be NULL (= zeros, which is what the reference effectively uses: misc.py:15-17 looks for a key
+ * "shapeparams" no dataset has); coord [B,3], quat [B,4] (i, j, k, w).  xy_offset = 0.5 when the labels have not been
+ * through offset_points_by_half_pixel yet (batch/normalization.py:83-90), else 0. */
+int b200aug_head_roi(const float* vertices, const float* deform_base, int32_t n_vertices, int32_t n_params,
+                     const float* shapeparams, const float* coord, const float* quat, float xy_offset, float* roi_out,
+                     int32_t batch, void* stream);
+
 /* torchquaternion.tomatrix (to_matrix != 0: in [B,4] xyzw -> out [B,3,3]; torchquaternion.py:70-91, the matrix / 6D
  * rotation target of losses.py:53-58) or torchquaternion.from_matrix (to_matrix == 0: in [B,3,3] -> out [B,4]; :94-168). */
 int b200aug_quat_matrix(const float* in, float* out, int batch, int to_matrix, void* stream);

@@ -2672,6 +2672,103 @@ __global__ void quat_matrix_kernel(const float* __restrict__ in, float* __restri
   }
 }
 
+// PutRoiFromLandmarks(extend_to_forehead=True), batch/misc.py:14-26: the roi is the xy bounding box of ALL vertices of the
+// posed deformable face model -- PosedDeformableHead (modelcomponents.py:85-94): local = vertices + sum_k base[k] * shape[k]
+// (ScaledBfmModule.forward, bfm.py:91-95), rotated by the pose quaternion, scaled by coord[2], shifted by coord[:2]
+// (rigid_transformation_25d, modelcomponents.py:38-56).  One CTA takes HR_SPB samples and walks the vertex list once for all
+// of them, so a deformation base entry is read once per HR_SPB samples; without shape parameters (what the reference does for
+// every dataset: it looks for a key "shapeparams" that no sample has) the inner loop disappears and the whole thing is a
+// min / max over 38 k rotated points.  `xy_offset` = the half-pixel shift offset_points_by_half_pixel would have applied to
+// coord in front of this transform (normalization.py:83-90), 0 when the caller already did.
+constexpr int HR_SPB = 8;
+constexpr int HR_MAXK = 64;
+
+__global__ void __launch_bounds__(NTHREADS) head_roi_kernel(const float* __restrict__ vertices, const float* __restrict__ deform_base,
+                                                            int V, int K, const float* __restrict__ shapeparams,
+                                                            const float* __restrict__ coord, const float* __restrict__ quat,
+                                                            float xy_offset, float* __restrict__ roi_out, int B) {
+  __shared__ float sp[HR_MAXK][HR_SPB];
+  __shared__ float pose[HR_SPB][12];  // rotation matrix (row-major), scale, tx, ty
+  __shared__ float red[NWARPS][HR_SPB][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s0 = blockIdx.x * HR_SPB, ns = min(HR_SPB, B - s0);
+  const bool deform = K > 0 && shapeparams != nullptr && deform_base != nullptr;
+  for (int i = tid; i < HR_MAXK * HR_SPB; i += NTHREADS) {
+    const int k = i / HR_SPB, s = i % HR_SPB;
+    sp[k][s] = (deform && k < K && s < ns) ? shapeparams[(size_t)(s0 + s) * K + k] : 0.f;
+  }
+  if (tid < HR_SPB) {
+    const int b = s0 + min(tid, ns - 1);
+    const float qi = quat[4 * (size_t)b], qj = quat[4 * (size_t)b + 1], qk = quat[4 * (size_t)b + 2], qw = quat[4 * (size_t)b + 3];
+    float* o = pose[tid];
+    o[0] = sub(1.f, mul(2.f, add(mul(qj, qj), mul(qk, qk))));
+    o[1] = mul(2.f, sub(mul(qi, qj), mul(qk, qw)));
+    o[2] = mul(2.f, add(mul(qi, qk), mul(qj, qw)));
+    o[3] = mul(2.f, add(mul(qi, qj), mul(qk, qw)));
+    o[4] = sub(1.f, mul(2.f, add(mul(qi, qi), mul(qk, qk))));
+    o[5] = mul(2.f, sub(mul(qj, qk), mul(qi, qw)));
+    o[9] = coord[3 * (size_t)b + 2];
+    o[10] = add(coord[3 * (size_t)b], xy_offset);
+    o[11] = add(coord[3 * (size_t)b + 1], xy_offset);
+  }
+  __syncthreads();
+  float lo_x[HR_SPB], lo_y[HR_SPB], hi_x[HR_SPB], hi_y[HR_SPB];
+#pragma unroll
+  for (int s = 0; s < HR_SPB; ++s) {
+    lo_x[s] = lo_y[s] = INFINITY;
+    hi_x[s] = hi_y[s] = -INFINITY;
+  }
+  for (int v = tid; v < V; v += NTHREADS) {
+    const float vx = vertices[3 * (size_t)v], vy = vertices[3 * (size_t)v + 1], vz = vertices[3 * (size_t)v + 2];
+    float ax[HR_SPB], ay[HR_SPB], az[HR_SPB];
+#pragma unroll
+    for (int s = 0; s < HR_SPB; ++s) ax[s] = ay[s] = az[s] = 0.f;
+    if (deform) {
+      for (int k = 0; k < K; ++k) {
+        const float* bp = deform_base + ((size_t)k * V + v) * 3;
+        const float bx = bp[0], by = bp[1], bz = bp[2];
+#pragma unroll
+        for (int s = 0; s < HR_SPB; ++s) {
+          const float w = sp[k][s];
+          ax[s] = __fmaf_rn(bx, w, ax[s]);
+          ay[s] = __fmaf_rn(by, w, ay[s]);
+          az[s] = __fmaf_rn(bz, w, az[s]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < HR_SPB; ++s) {
+      const float x = add(ax[s], vx), y = add(ay[s], vy), z = add(az[s], vz);
+      const float* o = pose[s];
+      const float rx = __fmaf_rn(o[2], z, __fmaf_rn(o[1], y, mul(o[0], x)));
+      const float ry = __fmaf_rn(o[5], z, __fmaf_rn(o[4], y, mul(o[3], x)));
+      const float px = add(mul(rx, o[9]), o[10]), py = add(mul(ry, o[9]), o[11]);
+      lo_x[s] = fminf(lo_x[s], px); hi_x[s] = fmaxf(hi_x[s], px);
+      lo_y[s] = fminf(lo_y[s], py); hi_y[s] = fmaxf(hi_y[s], py);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < HR_SPB; ++s) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo_x[s] = fminf(lo_x[s], __shfl_xor_sync(0xffffffffu, lo_x[s], d));
+      lo_y[s] = fminf(lo_y[s], __shfl_xor_sync(0xffffffffu, lo_y[s], d));
+      hi_x[s] = fmaxf(hi_x[s], __shfl_xor_sync(0xffffffffu, hi_x[s], d));
+      hi_y[s] = fmaxf(hi_y[s], __shfl_xor_sync(0xffffffffu, hi_y[s], d));
+    }
+    if (lane == 0) {
+      red[warp][s][0] = lo_x[s]; red[warp][s][1] = lo_y[s]; red[warp][s][2] = hi_x[s]; red[warp][s][3] = hi_y[s];
+    }
+  }
+  __syncthreads();
+  if (tid < HR_SPB * 4 && tid / 4 < ns) {
+    const int s = tid / 4, c = tid % 4;
+    float r = red[0][s][c];
+    for (int w = 1; w < NWARPS; ++w) r = (c < 2) ? fminf(r, red[w][s][c]) : fmaxf(r, red[w][s][c]);
+    roi_out[4 * (size_t)(s0 + s) + c] = r;
+  }
+}
+
 static thread_local int g_last_cuda_error = 0;
 
 extern "C" int b200aug_abi_version(void) { return B200AUG_ABI_VERSION; }
@@ -2947,6 +3044,20 @@ extern "C" int b200aug_corrected_rotation(const float* half_sizes, int64_t size_
   if (batch == 0) return B200AUG_OK;
   corrected_rotation_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(half_sizes, size_stride, div_x, div_y, f, coord,
                                                                                   coord_stride, pose, out, look_at_out, batch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  return B200AUG_OK;
+}
+
+extern "C" int b200aug_head_roi(const float* vertices, const float* deform_base, int32_t n_vertices, int32_t n_params,
+                                const float* shapeparams, const float* coord, const float* quat, float xy_offset, float* roi_out,
+                                int32_t batch, void* stream) {
+  if (!vertices || n_vertices <= 0 || !coord || !quat || !roi_out || batch < 0) return B200AUG_E_INVALID_ARG;
+  if (n_params < 0 || n_params > HR_MAXK) return B200AUG_E_INVALID_ARG;
+  if (shapeparams && n_params > 0 && !deform_base) return B200AUG_E_INVALID_ARG;
+  if (batch == 0) return B200AUG_OK;
+  head_roi_kernel<<<(batch + HR_SPB - 1) / HR_SPB, NTHREADS, 0, (cudaStream_t)stream>>>(vertices, deform_base, n_vertices, n_params,
+                                                                                          shapeparams, coord, quat, xy_offset, roi_out, batch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
   return B200AUG_OK;

@@ -64,10 +64,17 @@ def draw_photo_params(B: int, seed: int, sample_offset: int) -> E.PhotoParams:
 class FusedPoseAugmentation:
     def __init__(self, inputsize: int = 129, rotation_aug_angle: float = 30.0, roi_override: str = "original",
                  enable_image_aug: bool = True, train: bool = True, p_rot: float = 0.01, device="cuda",
-                 seed: int = 0, rowbuf_capacity: int = 0, zero_copy_frames: bool = False, upload_row_bands: bool = True):
-        if roi_override not in ("original", "landmarks"):
-            raise N.NativeError("roi_override='extent_to_forehead' needs the BFM face model and is not on the B200 path")
-        ext = {"original": 1.1, "landmarks": 1.2}[roi_override]  # pipelines.py:334
+                 seed: int = 0, rowbuf_capacity: int = 0, zero_copy_frames: bool = False, upload_row_bands: bool = True,
+                 headmodel=None):
+        if roi_override not in ("original", "landmarks", "extent_to_forehead"):
+            raise ValueError(f"got {roi_override}")  # pipelines.py:331
+        ext = {"original": 1.1, "extent_to_forehead": 1.1, "landmarks": 1.2}[roi_override]  # pipelines.py:334
+        # pipelines.py:352-356: the roi comes from the posed face model (needs the reference's BFM data), is not regenerated
+        self.headmodel = None
+        if roi_override == "extent_to_forehead":
+            from ..facemodel import HeadModel
+
+            self.headmodel = headmodel if headmodel is not None else HeadModel.default()
         self.inputsize = inputsize
         self.train = train
         self.p_rot = p_rot
@@ -184,7 +191,7 @@ class FusedPoseAugmentation:
         cats = batch.meta.categories
         img_keys = [k for k, v in batch.items() if E.as_category(cats.get(k)) == E.FieldCategory.image]
         ok = (self.upload_row_bands and (self.flags & N.F_FOCUS) and not (self.flags & N.F_ROI_FROM_LANDMARKS) and len(img_keys) == 1
-              and "roi" in batch.keys())
+              and "roi" in batch.keys() and self.headmodel is None)  # (the bands follow the roi, which must be known on the host)
         img = batch[img_keys[0]] if ok else None
         ok = ok and isinstance(img, torch.Tensor) and img.dtype == torch.uint8 and not img.is_cuda and img.is_pinned() and img.is_contiguous() \
             and (img.dim() == 3 or (img.dim() == 4 and (img.shape[-1] == 1 or img.shape[1] == 1)))
@@ -216,6 +223,12 @@ class FusedPoseAugmentation:
         src_batch = batch
         if batch.device != self.device:
             batch = self._upload(batch, d)
+        if self.headmodel is not None and "pt3d_68" in batch:
+            # PutRoiFromLandmarks(extend_to_forehead=True) behind offset_points_by_half_pixel (pipelines.py:352-353, 372): the
+            # kernel applies the half-pixel shift to the labels itself, so the head box gets it as an argument
+            batch = batch.__class__(batch.meta, dict(batch.items()))
+            batch["roi"] = self.headmodel.roi(batch["coord"], batch["pose"], batch["shapeparam"] if "shapeparams" in batch else None,
+                                              xy_offset=0.5)
         res = E.fused_forward(batch, flags=self.flags, out_size=self.inputsize, geo=d.geo, do_flip=d.do_flip,
                               rot_dir=d.rot_dir, photo=d.photo, rowbuf_capacity=self.rowbuf_capacity, want_status=True)
         self.status.watch(res.status, "FusedPoseAugmentation")
