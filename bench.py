@@ -422,13 +422,14 @@ def run_gpu_arm(args):
     host_outs = [host_out, {k: torch.empty_like(v).pin_memory() for k, v in host_out.items()}]
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
 
-    def measure_e2e(zero_copy: bool, pipelined: bool, bands: bool = False):
+    def measure_e2e(zero_copy: bool, pipelined: bool, bands: bool = False, boxes: bool = False):
         """Public API from pinned host buffers: per step the host->device copy of the step's frames + labels, the fused
         launch, and the device->host read of the step's labels.  pipelined: two streams alternate, the host waits for step
         s - 1 after enqueuing step s (what a prefetching loader does), so the copy engine never idles; otherwise one stream,
         synchronised every step.  zero_copy: the frames stay in pinned host memory and the kernel reads them in place."""
         aug = FusedPoseAugmentation(OUT, rotation_aug_angle=30.0, roi_override="original", enable_image_aug=True, device=dev,
                                     zero_copy_frames=zero_copy, upload_row_bands=bands)
+        aug.upload_boxes = boxes  # 2-D copies of the touched boxes, or whole row bands
         rows, host_ms = [], []
 
         def e2e_step(s):
@@ -436,7 +437,7 @@ def run_gpu_arm(args):
             st = streams[s % 2] if pipelined else torch.cuda.current_stream(dev)
             with torch.cuda.stream(st):
                 out = aug(pinned[s % 2])
-                rows.append(aug.uploaded_rows)
+                rows.append(aug.uploaded_bytes)
                 for k in label_keys:
                     host_outs[s % 2][k].copy_(out[k], non_blocking=True)
             host_ms.append((time.perf_counter() - t_h) * 1e3)  # host work of the step: sampling, marshalling, enqueueing
@@ -469,10 +470,13 @@ def run_gpu_arm(args):
 
     e2e = measure_e2e(False, True, bands=True)
     e2e_value, band_rows = e2e["value"], e2e["rows"]
-    h2d = label_bytes + int(band_rows * SRC)
+    h2d = label_bytes + int(band_rows)
     e2e_variants = {}
     if world == 1 and not args.quick:  # the other ways of getting the frames across, for the record (single GPU only)
+        boxes_2d = measure_e2e(False, True, bands=True, boxes=True)
         e2e_variants = {
+            "boxes_2d": {"value": boxes_2d["value"], "h2d_bytes_per_step": label_bytes + int(boxes_2d["rows"]),
+                         "note": "same, only the columns of the touched boxes copied (b200aug_upload_boxes, one batched 2-D copy)"},
             "whole_frames": {"value": measure_e2e(False, True)["value"], "h2d_bytes_per_step": label_bytes + frame_bytes,
                              "note": "same, whole frames copied (upload_row_bands=False)"},
             "whole_frames_synchronised_every_step": {"value": measure_e2e(False, False)["value"]},

@@ -242,6 +242,12 @@ int b200aug_hamming_table(const double* windows, float* taps_out, uint64_t* sym_
 int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
                              int32_t batch, const int32_t* row_lo, const int32_t* row_hi, void* stream);
 
+/* The same for boxes: rows [y0, y1) x columns [x0, x1) of frame i (boxes = HOST int32 [batch,4] = x0, y0, x1, y1, already
+ * clipped to the frame) -- one batched 2-D copy (cudaMemcpy3DBatchAsync), i.e. only the pixels the view boxes can touch
+ * cross PCIe. */
+int b200aug_upload_boxes(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch, int32_t batch,
+                         const int32_t* boxes, void* stream);
+
 /* The fused hot path.  Two kernels (three with an anti-alias prefilter) on `stream`, the second behind a programmatic
  * dependent launch:
  *   plan_kernel   one small CTA per sample: view box, transforms, cv2 resize tables, all label transforms, side outputs

@@ -2862,6 +2862,53 @@ extern "C" int b200aug_upload_row_bands(uint8_t* dev_frames, const uint8_t* host
   return B200AUG_OK;
 }
 
+extern "C" int b200aug_upload_boxes(uint8_t* dev_frames, const uint8_t* host_frames, int64_t frame_stride, int32_t pitch,
+                                    int32_t batch, const int32_t* boxes, void* stream) {
+  if (!dev_frames || !host_frames || frame_stride <= 0 || pitch <= 0 || batch < 0 || !boxes) return B200AUG_E_INVALID_ARG;
+  static thread_local std::vector<cudaMemcpy3DBatchOp> ops;
+  ops.clear();
+  ops.reserve(batch);
+  for (int i = 0; i < batch; ++i) {
+    const int64_t x0 = boxes[4 * i], y0 = boxes[4 * i + 1], x1 = boxes[4 * i + 2], y1 = boxes[4 * i + 3];
+    if (x0 < 0 || y0 < 0 || x1 > pitch || y1 * pitch > frame_stride) return B200AUG_E_INVALID_ARG;
+    if (x1 <= x0 || y1 <= y0) continue;
+    const int64_t off = (int64_t)i * frame_stride + y0 * pitch + x0;
+    cudaMemcpy3DBatchOp op = {};
+    op.src.type = cudaMemcpyOperandTypePointer;
+    op.src.op.ptr.ptr = const_cast<uint8_t*>(host_frames) + off;
+    op.src.op.ptr.rowLength = (size_t)pitch;
+    op.src.op.ptr.layerHeight = (size_t)(y1 - y0);
+    op.src.op.ptr.locHint.type = cudaMemLocationTypeHost;
+    op.dst.type = cudaMemcpyOperandTypePointer;
+    op.dst.op.ptr.ptr = dev_frames + off;
+    op.dst.op.ptr.rowLength = (size_t)pitch;
+    op.dst.op.ptr.layerHeight = (size_t)(y1 - y0);
+    op.dst.op.ptr.locHint.type = cudaMemLocationTypeDevice;
+    op.extent = make_cudaExtent((size_t)(x1 - x0), (size_t)(y1 - y0), 1);
+    op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    ops.push_back(op);
+  }
+  if (ops.empty()) return B200AUG_OK;
+  cudaError_t e = cudaErrorNotSupported;
+  static const bool one_by_one = getenv("B200AUG_UPLOAD_ONE_BY_ONE") != nullptr;
+  if (stream && !one_by_one) {
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    for (auto& op : ops) op.dst.op.ptr.locHint.id = dev;
+    size_t fail = 0;
+    e = cudaMemcpy3DBatchAsync(ops.size(), ops.data(), &fail, 0, (cudaStream_t)stream);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+  }
+  if (e != cudaSuccess) {  // (legacy default stream, or a driver without the batched entry point)
+    for (const auto& op : ops) {
+      e = cudaMemcpy2DAsync(op.dst.op.ptr.ptr, (size_t)pitch, op.src.op.ptr.ptr, (size_t)pitch, op.extent.width, op.extent.height,
+                            cudaMemcpyHostToDevice, (cudaStream_t)stream);
+      if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+    }
+  }
+  return B200AUG_OK;
+}
+
 static int check_fields(int n, const B200AugField* f) {
   if (n < 0 || n > B200AUG_MAX_FIELDS) return B200AUG_E_INVALID_ARG;
   for (int i = 0; i < n; ++i) {

@@ -53,7 +53,7 @@ class FusedArgs(C.Structure):
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_hamming_table", "b200aug_upload_row_bands", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
+           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_hamming_table", "b200aug_upload_row_bands", "b200aug_upload_boxes", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
            "b200aug_quat_matrix", "b200aug_head_roi", "b200aug_jpeg_info", "b200aug_decode_jpeg_gray", "b200aug_jpeg_last_status", "b200aug_jpeg_backend")
 
 
@@ -79,6 +79,8 @@ def _load():
     lib.b200aug_plan_buffer_bytes.restype = C.c_int64
     lib.b200aug_plan_buffer_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.b200aug_upload_row_bands.restype = C.c_int
+    lib.b200aug_upload_boxes.restype = C.c_int
+    lib.b200aug_upload_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.b200aug_upload_row_bands.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200aug_fused_forward.restype = C.c_int
     lib.b200aug_fused_forward.argtypes = [C.POINTER(FusedArgs), C.c_void_p]

@@ -77,7 +77,7 @@ def run(mode: str, workers: int, batches: int, batch: int):
             b = b.__class__(b.meta, {**dict(b.items()), "image": pre.imdecode_batch([x.numpy() for x in blobs], device=dev, stack=True)})
             return aug(b.to(dev, non_blocking=True))
         out = aug(b)  # stacked [B, 450, 450] uint8, pinned by the loader's pin_memory thread: row-band upload + one launch
-        h2d[0] += aug.uploaded_rows * 450
+        h2d[0] += aug.uploaded_bytes
         return out
 
     ds = RawDataset(batch * (batches + 4), mode)

@@ -229,10 +229,10 @@ def test_full_size_config2_properties():
 
 
 def test_upload_modes_agree():
-    """Three ways of getting pinned host frames to the kernel give bit-identical results: whole frames copied
-    (Batch.to), only the row bands of the sampled view boxes copied (b200aug_upload_row_bands; the rest of the device
-    frame stack holds stale rows of the previous batch), and frames read in place from pinned host memory.  Pageable
-    host frames are refused by the engine."""
+    """Four ways of getting pinned host frames to the kernel give bit-identical results: whole frames copied
+    (Batch.to), only the boxes the sampled view boxes can touch (b200aug_upload_boxes, 2-D copies) or their whole row bands
+    (b200aug_upload_row_bands) -- the rest of the device frame stack holds stale pixels of the previous batches --, and frames
+    read in place from pinned host memory.  Pageable host frames are refused by the engine."""
     import bench
     from trackertraincode_b200 import _native as N
     from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
@@ -241,11 +241,13 @@ def test_upload_modes_agree():
     B = 128
     cats = {k: FieldCategory(v) for k, v in bench.CATS.items()}
     augs = {m: FusedPoseAugmentation(S, rotation_aug_angle=30.0, device="cuda", seed=5, zero_copy_frames=(m == "zero_copy"),
-                                     upload_row_bands=(m == "bands")) for m in ("copy", "bands", "zero_copy")}
+                                     upload_row_bands=(m in ("bands", "boxes"))) for m in ("copy", "bands", "boxes", "zero_copy")}
+    augs["bands"].upload_boxes, augs["boxes"].upload_boxes = False, True
     for rnd in range(3):  # the band uploads of later rounds land in a frame stack full of the earlier rounds' rows
         host = bench.make_host_batch(9 + rnd, B)
         if rnd == 1:  # boxes hanging over the frame borders
             host["roi"][:, [1, 3]] += np.where(np.arange(B) % 2 == 0, -120.0, 150.0).astype(np.float32)[:, None]
+            host["roi"][:, [0, 2]] += np.where(np.arange(B) % 3 == 0, -130.0, 140.0).astype(np.float32)[:, None]
         pinned = Batch(Metadata((bench.SRC, bench.SRC), B, "t", None, dict(cats)), {k: torch.from_numpy(v).pin_memory() for k, v in host.items()})
         outs = {}
         for m, aug in augs.items():
@@ -254,7 +256,8 @@ def test_upload_modes_agree():
             draws = aug.draw(B)
             outs[m] = aug(pinned, params=draws)
         assert 0 < augs["bands"].uploaded_rows < 0.8 * B * bench.SRC
-        for m in ("bands", "zero_copy"):
+        assert 0 < augs["boxes"].uploaded_bytes < 0.8 * augs["bands"].uploaded_bytes
+        for m in ("bands", "boxes", "zero_copy"):
             assert outs[m]["image"].is_cuda and torch.equal(outs[m]["image"], outs["copy"]["image"]), (rnd, m)
             for k in ("roi", "coord", "pose", "pt3d_68"):
                 assert torch.equal(outs[m][k], outs["copy"][k]), (rnd, m, k)

@@ -233,7 +233,8 @@ def test_fused_augmentation_video_draws_and_row_bands():
     wh = rng.uniform(147, 250, (B, 2))
     c = 225 + rng.uniform(-140, 140, (B, 2))  # many boxes hang over the frame
     roi = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
-    lo, hi = aug._row_bands(torch.from_numpy(roi), d, 450)
+    boxes = aug._touched_boxes(torch.from_numpy(roi), d, 450, 450)
+    lo, hi = boxes[:, 1], boxes[:, 3]
     v = ogeo.round_view_roi(ogeo.compute_view_roi(roi, d.geo.scales.numpy(), d.geo.translations.numpy())).astype(np.int64)
     rot = d.geo.angles.numpy() != 0
     side = (v[:, 2] - v[:, 0]).astype(np.float64)
@@ -245,3 +246,12 @@ def test_fused_augmentation_video_draws_and_row_bands():
     touched = need_hi > need_lo
     assert (lo[touched] <= need_lo[touched]).all() and (hi[touched] >= need_hi[touched]).all()
     assert lo.dtype == np.int32 and (hi >= lo).all() and (hi - lo).sum() < 0.75 * B * 450
+    # the same along x (the boxes of b200aug_upload_boxes); columns come in multiples of 16
+    cx = 0.5 * (v[:, 0] + v[:, 2])
+    halfx = np.where(rot, 0.5 * side * (np.cos(ang) + np.sin(ang)) + 1.0, 0.5 * (v[:, 2] - v[:, 0]))
+    need_x0, need_x1 = np.clip(np.floor(cx - halfx), 0, 450), np.clip(np.ceil(cx + halfx) + 1, 0, 450)
+    touched = touched & (need_x1 > need_x0)
+    assert (boxes[touched, 0] <= need_x0[touched]).all() and (boxes[touched, 2] >= need_x1[touched]).all()
+    assert (boxes[:, 0] % 16 == 0).all() and (boxes[:, 2] >= boxes[:, 0]).all() and boxes[:, 2].max() <= 450
+    area = ((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])).sum()
+    assert area < 0.5 * B * 450 * 450
