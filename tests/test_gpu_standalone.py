@@ -167,8 +167,8 @@ def test_ragged_collation_into_fused_augmentation():
 
 
 def test_full_size_config2_properties():
-    """B=512, 450x450 -> 129x129 (BASELINE.json configs[1]): properties that do not need the oracle at full size, plus the
-    oracle on a random subset."""
+    """B=512, 450x450 -> 129x129 (BASELINE.json configs[1]): size-independent properties, and the oracle's full chain on every
+    one of the 512 samples."""
     import bench
     from trackertraincode_b200 import _native as N
     from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
@@ -215,17 +215,21 @@ def test_full_size_config2_properties():
     gp.do_flip[:] = saved
     norot = torch.from_numpy(gp.rot_dir == 0).cuda()
     assert torch.equal(a[norot].flip(-1), b[norot])
-    # (5) the oracle on a random subset, full chain
-    idx = np.random.default_rng(0).choice(B, 24, replace=False)
+    # (5) the oracle on all 512 samples, full chain
+    idx = np.arange(B)
+    img_host, pts_host = img.cpu().numpy(), whole.batch["pt3d_68"].cpu().numpy()
+    worst = 0.0
     samples = [Sample((bench.SRC, bench.SRC), {k: (host[k][i][..., None] if k == "image" else host[k][i]) for k in bench.CATS}, bench.CATS) for i in idx]
     g = opipe.GeoParams(gp.scales[idx], gp.angles[idx], gp.translations[idx], gp.do_flip[idx], gp.rot_dir[idx])
     for j, i in enumerate(idx):
         p1 = pp.slice(int(i), int(i) + 1)
         g1 = opipe.GeoParams(*(x[j:j + 1] for x in (g.scales, g.angles, g.translations, g.do_flip, g.rot_dir)))
         want, _ = opipe.augment_batch(samples[j:j + 1], g1, p1, S)
-        err = np.abs(img[i].cpu().numpy() - want["image"][0]).max()
+        err = np.abs(img_host[i] - want["image"][0]).max()
+        worst = max(worst, float(err))
         assert err <= 1.0 / 255, (i, err)
-        np.testing.assert_allclose(whole.batch["pt3d_68"][i].cpu().numpy(), want["pt3d_68"][0], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(pts_host[i], want["pt3d_68"][0], rtol=1e-4, atol=2e-5)
+    assert worst <= 1e-6  # (observed: the float32 photometric chain agrees to the last bit or two; 1/255 is the contract)
 
 
 def test_upload_modes_agree():
