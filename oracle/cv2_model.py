@@ -345,3 +345,160 @@ def antialias_prefilter_u8(img: np.ndarray, scale_factor: float, kind: str) -> n
     if kind == "hamming":
         return sep_filter_u8(img, hamming_kernel(scale_factor))
     raise NotImplementedError(kind)
+
+
+# ----------------------------------------------------------------------------- the cubic / Lanczos up-filters
+# trackertraincode/datatransformation/tensors/image_geometric_cv2.py:65-82 (cv2.resize with INTER_CUBIC / INTER_LANCZOS4 when a
+# crop grows) and :105-119 (cv2.warpAffine with those flags when the transform up-scales).  OpenCV's own 8-bit kernels are
+# fixed point and restated here bit for bit.  One caveat, checked in tests/test_oracle_upfilters.py: the x86 wheels route
+# cv2.resize(INTER_CUBIC) through Intel IPP, whose proprietary cubic differs from OpenCV's by at most 1 grey level on ~4 % of
+# the pixels (cv2.ipp.setUseIPP(False) gives the OpenCV kernel, and the model is bit-exact against it); INTER_LANCZOS4 and both
+# warpAffine modes run OpenCV's kernels with or without IPP.
+
+REMAP_COEF_BITS = 15
+INTER_TAB_SIZE = 32
+
+
+def cubic_coeffs(x) -> np.ndarray:
+    """cv::interpolateCubic (A = -0.75), float32, operation for operation."""
+    F = np.float32
+    x, A = F(x), F(-0.75)
+    c0 = ((A * (x + F(1)) - F(5) * A) * (x + F(1)) + F(8) * A) * (x + F(1)) - F(4) * A
+    c1 = ((A + F(2)) * x - (A + F(3))) * x * x + F(1)
+    c2 = ((A + F(2)) * (F(1) - x) - (A + F(3))) * (F(1) - x) * (F(1) - x) + F(1)
+    c3 = F(1) - c0 - c1 - c2
+    return np.array([c0, c1, c2, c3], F)
+
+
+_LANCZOS_CS = ((1.0, 0.0), (-0.70710678118654752440084436210485, -0.70710678118654752440084436210485), (0.0, 1.0),
+               (0.70710678118654752440084436210485, -0.70710678118654752440084436210485), (-1.0, 0.0),
+               (0.70710678118654752440084436210485, 0.70710678118654752440084436210485), (0.0, -1.0),
+               (-0.70710678118654752440084436210485, 0.70710678118654752440084436210485))
+
+
+def lanczos4_coeffs(x) -> np.ndarray:
+    """cv::interpolateLanczos4: sin / cos of the first tap's phase in double, the other taps by the angle-sum table, each
+    divided by its squared phase, the float32 results normalised by their float32 sum."""
+    F = np.float32
+    x = F(x)
+    if x < np.finfo(F).eps:
+        c = np.zeros(8, F)
+        c[3] = 1
+        return c
+    y0 = -(float(x) + 3) * np.pi * 0.25
+    s0, c0 = np.sin(y0), np.cos(y0)
+    c, s = np.zeros(8, F), F(0)
+    for i in range(8):
+        y = -(float(x) + 3 - i) * np.pi * 0.25
+        c[i] = F((_LANCZOS_CS[i][0] * s0 + _LANCZOS_CS[i][1] * c0) / (y * y))
+        s = F(s + c[i])
+    return (c * (F(1) / s)).astype(F)
+
+
+_KERNELS = {"cubic": (cubic_coeffs, 4), "lanczos": (lanczos4_coeffs, 8)}
+
+
+def resize_taps(ssize: int, dsize: int, kind: str):
+    """cv2.resize per-axis tables for the 4- / 8-tap kernels: first-tap offsets (before the border clamp) and 11-bit taps."""
+    coef, k = _KERNELS[kind]
+    scale = 1.0 / (float(dsize) / float(ssize))
+    ofs = np.zeros(dsize, np.int64)
+    taps = np.zeros((dsize, k), np.int64)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        taps[d] = np.rint(coef(f) * np.float32(1 << RESIZE_COEF_BITS)).astype(np.int64)
+        ofs[d] = s - (k // 2 - 1)
+    return ofs, taps
+
+
+def resize_cubic_or_lanczos_u8(src: np.ndarray, dw: int, dh: int, kind: str) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=INTER_CUBIC | INTER_LANCZOS4), u8 1-channel, OpenCV's own kernel: rows into
+    int32 with 11-bit taps (source indices clamped to the image); columns: Lanczos in integers, (sum + 2^21) >> 22; cubic in
+    float32 the way OpenCV's vector loop does it (VResizeCubicVec_32s8u: the row sums converted to float, taps scaled by
+    2^-22, s = r3 b3, s = fma(r2, b2, s), s = fma(r1, b1, s), s = fma(r0, b0, s), rint) -- its scalar loop for the last
+    `width mod 16` columns is the integer formula, which differs on the odd near-tie (about one pixel in 10^5)."""
+    assert src.dtype == np.uint8 and src.ndim == 2
+    sh, sw = src.shape
+    if (dw, dh) == (sw, sh):
+        return src.copy()
+    k = _KERNELS[kind][1]
+    xo, xc = resize_taps(sw, dw, kind)
+    yo, yc = resize_taps(sh, dh, kind)
+    S = src.astype(np.int64)
+    H = np.zeros((sh, dw), np.int64)
+    for t in range(k):
+        H += S[:, np.clip(xo + t, 0, sw - 1)] * xc[:, t][None, :]
+    if kind == "cubic":
+        F = np.float32
+        b = yc.astype(F) * (F(1.0) / F((1 << RESIZE_COEF_BITS) * (1 << RESIZE_COEF_BITS)))
+        rows = [H[np.clip(yo + t, 0, sh - 1)].astype(F) for t in range(4)]
+        acc = rows[3] * b[:, 3][:, None]
+        for t in (2, 1, 0):
+            acc = _fma32(rows[t], np.broadcast_to(b[:, t][:, None], acc.shape), acc)
+        return np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+    out = np.zeros((dh, dw), np.int64)
+    for t in range(k):
+        out += H[np.clip(yo + t, 0, sh - 1)] * yc[:, t][:, None]
+    return np.clip((out + (1 << (2 * RESIZE_COEF_BITS - 1))) >> (2 * RESIZE_COEF_BITS), 0, 255).astype(np.uint8)
+
+
+_REMAP_TABS = {}
+
+
+def remap_table(kind: str) -> np.ndarray:
+    """cv::initInterTab2D(fixpt): int64 [32, 32, k, k] -- for every 1/32-pixel phase (fy, fx) the outer product of the 1-D
+    float32 taps, scaled by 2^15 and rounded to short; if the k*k entries do not sum to 2^15 the difference goes to the
+    largest (sum too small) or smallest (too large) of the four entries [k/2 .. k/2+1]^2, exactly as OpenCV picks them."""
+    if kind in _REMAP_TABS:
+        return _REMAP_TABS[kind]
+    coef, k = _KERNELS[kind]
+    one = 1 << REMAP_COEF_BITS
+    t1 = np.stack([coef(np.float32(i) * np.float32(1.0 / INTER_TAB_SIZE)) for i in range(INTER_TAB_SIZE)])
+    tab = np.zeros((INTER_TAB_SIZE, INTER_TAB_SIZE, k, k), np.int64)
+    k2 = k // 2
+    for i in range(INTER_TAB_SIZE):
+        for j in range(INTER_TAB_SIZE):
+            v = (t1[i][:, None] * t1[j][None, :]).astype(np.float32)
+            it = np.clip(np.rint(v * np.float32(one)).astype(np.int64), -32768, 32767)
+            diff = int(it.sum()) - one
+            if diff != 0:
+                big, small = (k2, k2), (k2, k2)
+                for a in range(k2, k2 + 2):
+                    for b in range(k2, k2 + 2):
+                        if it[a, b] < it[small]:
+                            small = (a, b)
+                        elif it[a, b] > it[big]:
+                            big = (a, b)
+                if diff < 0:
+                    it[big] -= diff
+                else:
+                    it[small] -= diff
+            tab[i, j] = it
+    _REMAP_TABS[kind] = tab
+    return tab
+
+
+def warp_affine_cubic_or_lanczos_u8(src: np.ndarray, M, dw: int, dh: int, kind: str) -> np.ndarray:
+    """cv2.warpAffine(src, M, (dw, dh), flags=INTER_CUBIC | INTER_LANCZOS4, borderMode=BORDER_CONSTANT, borderValue=0): the
+    same 1/32-pixel fixed-point coordinates as the bilinear mode, k x k taps from remap_table, taps outside the image count
+    as 0, (sum + 2^14) >> 15."""
+    assert src.dtype == np.uint8 and src.ndim == 2
+    k = _KERNELS[kind][1]
+    tab = remap_table(kind)
+    X, Y = warp_affine_fixed_coords(M, dw, dh)
+    ix, iy, fx, fy = X >> INTER_BITS, Y >> INTER_BITS, X & (INTER_TAB_SIZE - 1), Y & (INTER_TAB_SIZE - 1)
+    sh, sw = src.shape
+    S = src.astype(np.int64)
+    o = k // 2 - 1
+    W = tab[fy, fx]
+    out = np.zeros((dh, dw), np.int64)
+    for a in range(k):
+        yy = iy - o + a
+        oky = (yy >= 0) & (yy < sh)
+        for b in range(k):
+            xx = ix - o + b
+            ok = oky & (xx >= 0) & (xx < sw)
+            out += np.where(ok, S[np.clip(yy, 0, sh - 1), np.clip(xx, 0, sw - 1)], 0) * W[:, :, a, b]
+    return np.clip((out + (1 << (REMAP_COEF_BITS - 1))) >> REMAP_COEF_BITS, 0, 255).astype(np.uint8)

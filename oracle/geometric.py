@@ -111,12 +111,19 @@ def antialias_prefilter(img: np.ndarray, scale_factor: float, kind: str, use_mod
     raise NotImplementedError(f"Filter: {kind}")
 
 
-def resize_area_or_linear(img: np.ndarray, new_w: int, new_h: int, use_model=False, downfilter="area") -> np.ndarray:
-    """_resize (image_geometric_cv2.py:65-82) with upfilter='linear': when the mean scale is < 1, INTER_AREA
-    (downfilter='area', the sampler's fixed choice, geometric.py:76-77) or the gaussian / hamming prefilter followed by
-    INTER_LINEAR; INTER_LINEAR otherwise."""
+_CV2_UP = {"linear": cv2.INTER_LINEAR, "cubic": cv2.INTER_CUBIC, "lanczos": cv2.INTER_LANCZOS4}
+
+
+def resize_area_or_linear(img: np.ndarray, new_w: int, new_h: int, use_model=False, downfilter="area", upfilter="linear") -> np.ndarray:
+    """_resize (image_geometric_cv2.py:65-82): when the mean scale is < 1, INTER_AREA (downfilter='area', the sampler's fixed
+    choice, geometric.py:76-77) or the gaussian / hamming prefilter followed by INTER_LINEAR; otherwise the up-filter
+    (INTER_LINEAR -- the sampler's choice --, INTER_CUBIC or INTER_LANCZOS4)."""
     old_h, old_w = img.shape[:2]
     scale_factor = 0.5 * (new_w / old_w + new_h / old_h)
+    if scale_factor >= 1.0 and upfilter != "linear":
+        if use_model:
+            return cv2_model.resize_cubic_or_lanczos_u8(img, new_w, new_h, upfilter)
+        return cv2.resize(img, dsize=(new_w, new_h), interpolation=_CV2_UP[upfilter])
     if scale_factor < 1.0 and downfilter in ("gaussian", "hamming"):
         img = antialias_prefilter(img, scale_factor, downfilter, use_model)
         if use_model:
@@ -129,10 +136,10 @@ def resize_area_or_linear(img: np.ndarray, new_w: int, new_h: int, use_model=Fal
     return cv2.resize(img, dsize=(new_w, new_h), interpolation=cv2.INTER_AREA if area else cv2.INTER_LINEAR)
 
 
-def croprescale_image(img: np.ndarray, roi, new_wh, use_model=False, downfilter="area") -> np.ndarray:
+def croprescale_image(img: np.ndarray, roi, new_wh, use_model=False, downfilter="area", upfilter="linear") -> np.ndarray:
     """croprescale_image_cv2 (image_geometric_cv2.py:138-155), [H, W] u8 in, [oh, ow] u8 out."""
     ow, oh = new_wh
-    return resize_area_or_linear(extract_roi_zero_padded(img, roi), ow, oh, use_model, downfilter)
+    return resize_area_or_linear(extract_roi_zero_padded(img, roi), ow, oh, use_model, downfilter, upfilter)
 
 
 def warp_plan(tr, new_wh):
@@ -152,24 +159,27 @@ def warp_plan(tr, new_wh):
     return M, rot_w, rot_h, False
 
 
-def affine_transform_image(img: np.ndarray, tr, new_wh, use_model=False, downfilter="area") -> np.ndarray:
-    """affine_transform_image_cv2: anti-aliased warpAffine = warp to an intermediate canvas, then area-resize."""
+def affine_transform_image(img: np.ndarray, tr, new_wh, use_model=False, downfilter="area", upfilter="linear") -> np.ndarray:
+    """affine_transform_image_cv2: an up-scaling transform warps straight to the output with the up-filter (:105-119);
+    otherwise anti-aliased = bilinear warp to an intermediate canvas at source resolution, then _resize (:120-134)."""
     ow, oh = new_wh
     M, cw, ch, up = warp_plan(tr, new_wh)
+    interp = upfilter if up else "linear"
     if use_model:
-        canvas = cv2_model.warp_affine_linear_u8(img, M, cw, ch)
+        canvas = (cv2_model.warp_affine_linear_u8(img, M, cw, ch) if interp == "linear"
+                  else cv2_model.warp_affine_cubic_or_lanczos_u8(img, M, cw, ch, interp))
     else:
-        canvas = cv2.warpAffine(img, M=M, dsize=(cw, ch), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=None)
+        canvas = cv2.warpAffine(img, M=M, dsize=(cw, ch), flags=_CV2_UP[interp], borderMode=cv2.BORDER_CONSTANT, borderValue=None)
     if up:
         return canvas
-    return resize_area_or_linear(canvas, ow, oh, use_model, downfilter)
+    return resize_area_or_linear(canvas, ow, oh, use_model, downfilter, upfilter)
 
 
 # ----------------------------------------------------------------------------- sample-level transforms
 
 
 def focus_roi(sample: Sample, params: RoiFocusParams, new_size, roi_variable="roi", insert_backtransform=False,
-              beyond_border_shift=0.3, use_model=False, downfilter="area") -> Tuple[Sample, dict]:
+              beyond_border_shift=0.3, use_model=False, downfilter="area", upfilter="linear") -> Tuple[Sample, dict]:
     """GeneralFocusRoi.__call__ (geometric.py:193-231) with explicit parameters.
 
     Returns the transformed sample and the intermediates the parity tests compare bit-exactly
@@ -186,9 +196,9 @@ def focus_roi(sample: Sample, params: RoiFocusParams, new_size, roi_variable="ro
         if c == CAT_IMAGE:
             img = v[..., 0] if v.ndim == 3 else v
             if F32(params.angle) != 0.0:
-                res = affine_transform_image(img, tr, new_wh, use_model, downfilter)
+                res = affine_transform_image(img, tr, new_wh, use_model, downfilter, upfilter)
             else:
-                res = croprescale_image(img, view_i, new_wh, use_model, downfilter)
+                res = croprescale_image(img, view_i, new_wh, use_model, downfilter, upfilter)
             out.data[k] = res[None, ...]
         elif c in IMAGELIKE:
             raise NotImplementedError("semseg fields are outside the hot path")
