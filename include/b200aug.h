@@ -76,6 +76,13 @@ extern "C" {
 #define B200AUG_DOWN_HAMMING 2    /* cv2.sepFilter2D with the normalised Hamming window of round(2 / scale + 1) taps (made
                                      odd): float32, the arithmetic of cv2's vector loops */
 #define B200AUG_PREFILTER_MAX_TAPS 63
+/* B200AugFusedArgs::upfilter -- UpFilters of tensors/image_geometric_cv2.py:16, used when a crop grows: the interpolation of
+ * cv2.resize (:68-75) or, for a rotated sample whose transform up-scales, of cv2.warpAffine (:105-119).  OpenCV's own
+ * fixed-point kernels, bit-exact (one caveat: x86 wheels route cv2.resize(INTER_CUBIC) through Intel IPP, which differs from
+ * OpenCV's kernel by at most one grey level on a few per cent of the pixels). */
+#define B200AUG_UP_LINEAR 0
+#define B200AUG_UP_CUBIC 1
+#define B200AUG_UP_LANCZOS 2
 
 #define B200AUG_PHASE_ALL 0
 #define B200AUG_PHASE_PLAN 1
@@ -206,7 +213,7 @@ typedef struct B200AugFusedArgs {
                                    the big kernel. */
 
   int32_t downfilter;           /* B200AUG_DOWN_*; anything but AREA needs `plans` and `workspace` (else E_UNSUPPORTED) */
-  int32_t reserved0;
+  int32_t upfilter;             /* B200AUG_UP_*; anything but LINEAR needs `remap_tabs` */
   /* B200AUG_DOWN_HAMMING: the normalised Hamming windows as float32, row r = (n - 1) / 2 of a [32][64] device table holds
    * the n = 2 r + 1 taps (scipy.signal.windows.hamming(n) / sum, evaluated on the host exactly as the reference does and
    * then rounded to float32, as cv2 does); bit r of hamming_sym_mask says whether the float64 window is exactly mirror
@@ -214,6 +221,9 @@ typedef struct B200AugFusedArgs {
    * decides).  b200aug_hamming_table() fills both from a given evaluation of the windows. */
   const float* hamming_taps;
   uint64_t hamming_sym_mask;
+  /* B200AUG_UP_CUBIC / _LANCZOS: cv2's fixed-point interpolation tables for warpAffine, device memory: 1024 x 16 shorts
+   * (cubic) followed by 1024 x 64 shorts (Lanczos), as b200aug_remap_table() computes them */
+  const int16_t* remap_tabs;
 
   B200AugPhotoParams photo;     /* read when F_PHOTOMETRIC is set */
 } B200AugFusedArgs;
@@ -233,6 +243,9 @@ int64_t b200aug_plan_buffer_bytes(int batch, int out_w, int out_h);
  * taps at windows[r * 64 .. r * 64 + n) for r = 1 .. 31 (row 0 unused); taps_out = HOST float32 [32 * 64] (copy it to the
  * device), *sym_mask_out = the symmetry bits.  Plain host code, no CUDA call. */
 int b200aug_hamming_table(const double* windows, float* taps_out, uint64_t* sym_mask_out);
+/* cv::initInterTab2D for B200AugFusedArgs::remap_tabs: out = HOST shorts, 1024 x 16 for B200AUG_UP_CUBIC, 1024 x 64 for
+ * B200AUG_UP_LANCZOS (phase (fy, fx) at (fy * 32 + fx) * k * k).  Plain host code, no CUDA call. */
+int b200aug_remap_table(int upfilter, int16_t* out);
 
 /* Host -> device upload of the rows the fused kernel will read, instead of whole frames (Batch.to(device),
  * datasets/batch.py:161-165 / pipelines.py:508): for each of `batch` stacked frames (host_frames: PINNED host memory,

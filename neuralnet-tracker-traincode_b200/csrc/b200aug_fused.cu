@@ -51,7 +51,7 @@ constexpr int DEFAULT_CLUSTER = 2;  // CTAs sharing one sample
 __host__ __device__ __forceinline__ int ring_slot_bytes(int seg_bytes) { return (seg_bytes + 15 + 15 + ROWBUF_SLACK) & ~15; }
 
 enum SrcMode { SRC_CROP = 0, SRC_WARP = 1, SRC_PLAIN = 2 };
-enum RsMode { RS_COPY = 0, RS_AREA = 1, RS_AREA_INT = 2, RS_LINEAR = 3 };
+enum RsMode { RS_COPY = 0, RS_AREA = 1, RS_AREA_INT = 2, RS_LINEAR = 3, RS_CUBIC = 4, RS_LANCZOS = 5 };
 
 struct Plan {
   // source
@@ -91,6 +91,11 @@ struct Plan {
   // scale factor the taps derive from
   int prefilter, pf_n;
   double pf_sf;
+  // up-filters cubic / lanczos (image_geometric_cv2.py:65-82,105-119): an up-scaling cv2.warpAffine runs with INTER_CUBIC /
+  // INTER_LANCZOS4 (warp_interp = B200AUG_UP_*, warp_tab = cv2's 32 x 32 table of k x k fixed-point taps for that mode);
+  // an up-scaling cv2.resize is rs_mode RS_CUBIC / RS_LANCZOS
+  int warp_interp, pad_up;
+  const int16_t* warp_tab;
 };
 
 constexpr size_t WORKER_AREA = 2 * 512 * 8 + 1024 * 2 + 128 + 32 * 48 + 3 * 9136;  // = WK_AREA_BYTES (checked where that is defined)
@@ -351,10 +356,17 @@ __device__ void plan_basic_and_warp(const B200AugFusedArgs& a, const PlanCore& c
   P.ch = c.ch;
   P.x0 = (c.src_mode == SRC_PLAIN) ? 0 : c.vx0;
   P.y0 = (c.src_mode == SRC_PLAIN) ? 0 : c.vy0;
+  P.warp_interp = 0;
+  P.pad_up = 0;
+  P.warp_tab = nullptr;
   if (c.src_mode == SRC_WARP) {
     Aff M;
     if (c.cw == ow && c.ch == oh && (double)aff_scales(c.t1) > 1.0) {
       M = aff_compose(c.t1, Aff{1.f, 0.f, 0.5f, 0.f, 1.f, 0.5f});
+      if (a.upfilter != B200AUG_UP_LINEAR && a.remap_tabs) {  // image_geometric_cv2.py:105-119: the up-filter is the warp's flag
+        P.warp_interp = a.upfilter;
+        P.warp_tab = a.remap_tabs + (a.upfilter == B200AUG_UP_CUBIC ? 0 : 1024 * 16);
+      }
     } else {
       float sc = (float)((double)c.ch / (double)oh);
       M = aff_compose(Aff{sc, 0.f, 0.f, 0.f, sc, 0.f}, c.t1);
@@ -426,7 +438,8 @@ __device__ void plan_resize(const B200AugFusedArgs& a, const PlanCore& c, Plan& 
         P.lin_area = 1;
       }
     } else {
-      P.rs_mode = RS_LINEAR;
+      // the up-filter (image_geometric_cv2.py:68-75)
+      P.rs_mode = (a.upfilter == B200AUG_UP_CUBIC) ? RS_CUBIC : ((a.upfilter == B200AUG_UP_LANCZOS) ? RS_LANCZOS : RS_LINEAR);
     }
   }
 }
@@ -625,6 +638,76 @@ __device__ void area_tab_entry(int d, double scale, int ssize, int& start, int& 
   nflags = n | (hf ? (1 << 30) : 0) | (hl ? (1u << 31) : 0);
 }
 
+// cv::interpolateCubic (A = -0.75) and cv::interpolateLanczos4, float32 / double exactly as OpenCV evaluates them
+// (oracle/cv2_model.py:cubic_coeffs, lanczos4_coeffs)
+__host__ __device__ inline void cubic_coeffs(float x, float* c) {
+  const float A = -0.75f;
+#ifdef __CUDA_ARCH__
+  const float x1 = __fadd_rn(x, 1.f), xm = __fsub_rn(1.f, x);
+  c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), __fmul_rn(5.f, A)), x1), __fmul_rn(8.f, A)), x1), __fmul_rn(4.f, A));
+  c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), x), __fadd_rn(A, 3.f)), x), x), 1.f);
+  c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), xm), __fadd_rn(A, 3.f)), xm), xm), 1.f);
+  c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
+#else
+  volatile float t;  // (volatile: every operation rounds to float32 on its own, whatever the host compiler would contract)
+  const float x1 = x + 1.f, xm = 1.f - x;
+  t = A * x1; t = t - 5.f * A; t = t * x1; t = t + 8.f * A; t = t * x1; t = t - 4.f * A; c[0] = t;
+  t = (A + 2.f) * x; t = t - (A + 3.f); t = t * x; t = t * x; t = t + 1.f; c[1] = t;
+  t = (A + 2.f) * xm; t = t - (A + 3.f); t = t * xm; t = t * xm; t = t + 1.f; c[2] = t;
+  t = 1.f - c[0]; t = t - c[1]; t = t - c[2]; c[3] = t;
+#endif
+}
+
+__host__ __device__ inline void lanczos4_coeffs(float x, float* c) {
+  const double s45 = 0.70710678118654752440084436210485;
+  const double cs[8][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  if (x < 1.1920929e-07f) {  // FLT_EPSILON
+    for (int i = 0; i < 8; ++i) c[i] = 0.f;
+    c[3] = 1.f;
+    return;
+  }
+  const double pi4 = 3.1415926535897932384626433832795 * 0.25;
+  const double y0 = -((double)x + 3) * pi4, s0 = sin(y0), c0 = cos(y0);
+#ifdef __CUDA_ARCH__
+  float sum = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const double y = -((double)x + 3 - i) * pi4;
+    c[i] = (float)__ddiv_rn(__dadd_rn(__dmul_rn(cs[i][0], s0), __dmul_rn(cs[i][1], c0)), __dmul_rn(y, y));
+    sum = __fadd_rn(sum, c[i]);
+  }
+  sum = __fdiv_rn(1.f, sum);
+  for (int i = 0; i < 8; ++i) c[i] = __fmul_rn(c[i], sum);
+#else
+  volatile float sum = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const double y = -((double)x + 3 - i) * pi4;
+    volatile double num = cs[i][0] * s0;
+    volatile double num2 = cs[i][1] * c0;
+    c[i] = (float)((num + num2) / (y * y));
+    sum = sum + c[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; ++i) { volatile float v = c[i] * sum; c[i] = v; }
+#endif
+}
+
+// cv::resize INTER_CUBIC / INTER_LANCZOS4 taps of one output coordinate (oracle/cv2_model.py:resize_taps): first tap index
+// (before the border clamp) and the k 11-bit taps, packed two shorts per word
+__device__ void kernel_tab_entry(int d, double scale, int k, int& first, uint32_t (&packed)[4]) {
+  float f = (float)((d + 0.5) * scale - 0.5);
+  const int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  float c[8];
+  if (k == 4) cubic_coeffs(f, c);
+  else lanczos4_coeffs(f, c);
+  int t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = (i < k) ? min(max(__float2int_rn(__fmul_rn(c[i], 2048.f)), -32768), 32767) : 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) packed[i] = ((uint32_t)t[2 * i] & 0xffffu) | ((uint32_t)t[2 * i + 1] << 16);
+  first = s - (k / 2 - 1);
+}
+
 // cv::resize INTER_LINEAR taps (oracle/cv2_model.py:linear_tab + border rules)
 __device__ void linear_tab_entry(int d, double scale, int ssize, int dsize, bool area_mode, bool is_x, int& i0, int& i1, int& w0, int& w1) {
   float f;
@@ -675,6 +758,23 @@ __device__ int canvas_px(const Plan& P, int x, int y) {
   const int bd = rint_d2i(__dmul_rn(__dmul_rn(P.mi[3], (double)x), 1024.0));
   const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
   const int ix = X >> 5, iy = Y >> 5, fx = X & 31, fy = Y & 31;
+  if (P.warp_interp != 0) {
+    // INTER_CUBIC / INTER_LANCZOS4 (oracle/cv2_model.py:warp_affine_cubic_or_lanczos_u8): k x k taps of cv2's fixed-point
+    // table for the 1/32-pixel phase, taps outside the image count as 0 (BORDER_CONSTANT), (sum + 2^14) >> 15
+    const int k = (P.warp_interp == B200AUG_UP_CUBIC) ? 4 : 8, o = k / 2 - 1;
+    const int16_t* w = P.warp_tab + (size_t)(fy * 32 + fx) * (k * k);
+    int sum = 0;
+    for (int r = 0; r < k; ++r) {
+      const int yy = iy - o + r;
+      if ((unsigned)yy >= (unsigned)P.sh) continue;
+      const uint8_t* row = P.src + (ptrdiff_t)yy * P.pitch;
+      for (int q = 0; q < k; ++q) {
+        const int xx = ix - o + q;
+        if ((unsigned)xx < (unsigned)P.sw) sum += (int)__ldg(row + xx) * (int)__ldg(w + r * k + q);
+      }
+    }
+    return min(max((sum + (1 << 14)) >> 15, 0), 255);
+  }
   const bool r0 = (iy >= 0) && (iy < P.sh), r1 = (iy + 1 >= 0) && (iy + 1 < P.sh);
   const bool c0 = (ix >= 0) && (ix < P.sw), c1 = (ix + 1 >= 0) && (ix + 1 < P.sw);
   const uint8_t* p = P.src + (ptrdiff_t)iy * P.pitch + ix;
@@ -730,6 +830,34 @@ __device__ __noinline__ uint8_t scalar_out_px(const Plan& P, const Tabs& T, int 
       const int h1 = canvas_px(P, x0, r1) * a0 + canvas_px(P, x1, r1) * a1;
       const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
       return (uint8_t)min(max(v, 0), 255);
+    }
+    case RS_CUBIC:
+    case RS_LANCZOS: {
+      // cv2.resize INTER_CUBIC / INTER_LANCZOS4 (oracle/cv2_model.py:resize_cubic_or_lanczos_u8): rows in int32 with 11-bit
+      // taps, source indices clamped to the canvas; columns: Lanczos in integers, cubic in float32 as OpenCV's vector loop
+      const int k = (P.rs_mode == RS_CUBIC) ? 4 : 8;
+      const int xs = T.start[dx], ys = T.start[ow + dy];
+      const uint32_t xw[4] = {(uint32_t)T.n[dx], __float_as_uint(T.a[dx]), __float_as_uint(T.b[dx]), __float_as_uint(T.c[dx])};
+      const uint32_t yw[4] = {(uint32_t)T.n[ow + dy], __float_as_uint(T.a[ow + dy]), __float_as_uint(T.b[ow + dy]), __float_as_uint(T.c[ow + dy])};
+      auto tap = [](const uint32_t (&w)[4], int i) { return (int)(int16_t)(w[i >> 1] >> (16 * (i & 1))); };
+      int hsum[8];
+      for (int r = 0; r < k; ++r) {
+        const int yy = min(max(ys + r, 0), P.ch - 1);
+        int h = 0;
+        for (int q = 0; q < k; ++q) h += canvas_px(P, min(max(xs + q, 0), P.cw - 1), yy) * tap(xw, q);
+        hsum[r] = h;
+      }
+      if (k == 4) {
+        const float sc = 1.f / (2048.f * 2048.f);
+        float acc = __fmul_rn((float)hsum[3], __fmul_rn((float)tap(yw, 3), sc));
+        acc = __fmaf_rn((float)hsum[2], __fmul_rn((float)tap(yw, 2), sc), acc);
+        acc = __fmaf_rn((float)hsum[1], __fmul_rn((float)tap(yw, 1), sc), acc);
+        acc = __fmaf_rn((float)hsum[0], __fmul_rn((float)tap(yw, 0), sc), acc);
+        return sat_u8_rint(acc);
+      }
+      long long v = 0;
+      for (int r = 0; r < 8; ++r) v += (long long)hsum[r] * tap(yw, r);
+      return (uint8_t)min(max((v + (1ll << 21)) >> 22, 0ll), 255ll);
     }
     default: return (uint8_t)canvas_px(P, dx, dy);  // RS_COPY
   }
@@ -1279,7 +1407,16 @@ __device__ __forceinline__ void build_plan(const B200AugFusedArgs& a, int b, Pla
 __device__ __forceinline__ void build_tables(const B200AugFusedArgs& a, Plan& P, const Tabs& T, int tid, int lane, int nthr) {
   const int ow = a.out_w, oh = a.out_h;
   const int rs = P.rs_mode;
-  if (rs == RS_AREA || rs == RS_LINEAR || rs == RS_AREA_INT) {
+  if (rs == RS_CUBIC || rs == RS_LANCZOS) {
+    for (int i = tid; i < ow + oh; i += nthr) {
+      const bool is_x = i < ow;
+      int first;
+      uint32_t packed[4];
+      kernel_tab_entry(is_x ? i : i - ow, is_x ? P.scale_x : P.scale_y, rs == RS_CUBIC ? 4 : 8, first, packed);
+      T.start[i] = first; T.n[i] = (int)packed[0]; T.a[i] = __uint_as_float(packed[1]); T.b[i] = __uint_as_float(packed[2]);
+      T.c[i] = __uint_as_float(packed[3]);
+    }
+  } else if (rs == RS_AREA || rs == RS_LINEAR || rs == RS_AREA_INT) {
     // two independent entries per thread and iteration: 129 + 129 entries on 256 threads would otherwise pay a second,
     // nearly empty, round of double-precision latency
     auto tab_entry = [&](int i) {
@@ -1393,7 +1530,8 @@ __global__ void __launch_bounds__(NTHREADS) plan_kernel(const __grid_constant__ 
           P.status = B200AUG_S_UNSUPPORTED;
         }
       }
-    } else if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.status == B200AUG_S_OK && P.cw <= DT_CAP && P.ch <= DT_CAP) {
+    } else if (with_tables && a.plans && a.workspace && a.warp_ctas > 0 && P.src_mode == SRC_WARP && P.warp_interp == 0 &&
+               P.status == B200AUG_S_OK && P.cw <= DT_CAP && P.ch <= DT_CAP) {  // (the workers' gather is the bilinear one)
       const int spitch = canvas_pitch(P.cw);
       if ((int64_t)spitch * (P.ch + 1) <= a.workspace_stride) {
         P.cv_ptr = a.workspace + (size_t)b * a.workspace_stride;
@@ -2810,6 +2948,44 @@ extern "C" int64_t b200aug_workspace_stride(int max_side) {
   return ((spitch * (max_side + 1)) + 255) & ~int64_t(255);
 }
 
+extern "C" int b200aug_remap_table(int upfilter, int16_t* out) {
+  // cv::initInterTab2D(fixpt) (oracle/cv2_model.py:remap_table): plain host code
+  if (!out || (upfilter != B200AUG_UP_CUBIC && upfilter != B200AUG_UP_LANCZOS)) return B200AUG_E_INVALID_ARG;
+  const int k = (upfilter == B200AUG_UP_CUBIC) ? 4 : 8, k2 = k / 2;
+  float t1[32][8];
+  for (int i = 0; i < 32; ++i) {
+    volatile float x = (float)i * (1.0f / 32);
+    if (k == 4) cubic_coeffs(x, t1[i]);
+    else lanczos4_coeffs(x, t1[i]);
+  }
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j) {
+      int16_t* it = out + (size_t)(i * 32 + j) * k * k;
+      int isum = 0;
+      for (int a = 0; a < k; ++a)
+        for (int b = 0; b < k; ++b) {
+          volatile float v = t1[i][a] * t1[j][b];
+          volatile float sv = v * 32768.f;
+          long r = lrintf(sv);
+          r = r < -32768 ? -32768 : (r > 32767 ? 32767 : r);
+          it[a * k + b] = (int16_t)r;
+          isum += (int)r;
+        }
+      if (isum != 32768) {
+        const int diff = isum - 32768;
+        int Mk1 = k2, Mk2 = k2, mk1 = k2, mk2 = k2;
+        for (int a = k2; a < k2 + 2; ++a)
+          for (int b = k2; b < k2 + 2; ++b) {
+            if (it[a * k + b] < it[mk1 * k + mk2]) { mk1 = a; mk2 = b; }
+            else if (it[a * k + b] > it[Mk1 * k + Mk2]) { Mk1 = a; Mk2 = b; }
+          }
+        if (diff < 0) it[Mk1 * k + Mk2] = (int16_t)(it[Mk1 * k + Mk2] - diff);
+        else it[mk1 * k + mk2] = (int16_t)(it[mk1 * k + mk2] - diff);
+      }
+    }
+  return B200AUG_OK;
+}
+
 extern "C" int b200aug_hamming_table(const double* windows, float* taps_out, uint64_t* sym_mask_out) {
   if (!windows || !taps_out || !sym_mask_out) return B200AUG_E_INVALID_ARG;
   uint64_t mask = 0;
@@ -2988,6 +3164,8 @@ extern "C" int b200aug_fused_forward(const B200AugFusedArgs* args, void* stream)
   // anti-alias prefilters keep their smoothed canvases in the workspace and are planned by plan_kernel
   const bool prefilter = want_image && (a.flags & B200AUG_F_FOCUS) && a.downfilter != B200AUG_DOWN_AREA;
   if (a.downfilter < B200AUG_DOWN_AREA || a.downfilter > B200AUG_DOWN_HAMMING) return B200AUG_E_INVALID_ARG;
+  if (a.upfilter < B200AUG_UP_LINEAR || a.upfilter > B200AUG_UP_LANCZOS) return B200AUG_E_INVALID_ARG;
+  if (a.upfilter != B200AUG_UP_LINEAR && (a.flags & B200AUG_F_FOCUS) && want_image && !a.remap_tabs) return B200AUG_E_INVALID_ARG;
   if (prefilter && a.downfilter == B200AUG_DOWN_HAMMING && !a.hamming_taps) return B200AUG_E_INVALID_ARG;
   if (prefilter && (!records || !a.workspace)) return B200AUG_E_UNSUPPORTED;
   if (a.phase < B200AUG_PHASE_ALL || a.phase > B200AUG_PHASE_MAIN) return B200AUG_E_INVALID_ARG;

@@ -15,6 +15,7 @@ F_HALF_PIXEL, F_ROI_FROM_LANDMARKS, F_FOCUS, F_FLIPROT, F_NORMALIZE, F_PHOTOMETR
 CAT_GENERAL, CAT_QUAT, CAT_XYS, CAT_ROI, CAT_POINTS, CAT_BACKTRANSFORM = 0, 1, 2, 3, 4, 5
 PHASE_ALL, PHASE_PLAN, PHASE_MAIN = 0, 1, 2
 DOWN_AREA, DOWN_GAUSSIAN, DOWN_HAMMING = 0, 1, 2
+UP_LINEAR, UP_CUBIC, UP_LANCZOS = 0, 1, 2
 PREFILTER_MAX_TAPS = 63
 S_OK, S_EMPTY_BOX, S_UNSUPPORTED, S_ROWBUF = 0, 1, 2, 3
 OP_EQUALIZE, OP_POSTERIZE, OP_GAMMA, OP_CONTRAST, OP_BRIGHTNESS, OP_BLUR = range(6)
@@ -48,12 +49,13 @@ class FusedArgs(C.Structure):
                 ("image_u8_out", C.c_void_p), ("image_f32_out", C.c_void_p), ("status_out", C.c_void_p),
                 ("trace_out", C.c_void_p), ("order", C.c_void_p), ("workspace", C.c_void_p), ("workspace_stride", C.c_int64),
                 ("plans", C.c_void_p), ("plan_stride", C.c_int64), ("warp_ctas", C.c_int32), ("phase", C.c_int32),
-                ("downfilter", C.c_int32), ("reserved0", C.c_int32), ("hamming_taps", C.c_void_p), ("hamming_sym_mask", C.c_uint64),
+                ("downfilter", C.c_int32), ("upfilter", C.c_int32), ("hamming_taps", C.c_void_p), ("hamming_sym_mask", C.c_uint64),
+                ("remap_tabs", C.c_void_p),
                 ("photo", PhotoParams)]
 
 
 EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
-           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_hamming_table", "b200aug_upload_row_bands", "b200aug_upload_boxes", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
+           "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_hamming_table", "b200aug_remap_table", "b200aug_upload_row_bands", "b200aug_upload_boxes", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
            "b200aug_quat_matrix", "b200aug_head_roi", "b200aug_jpeg_info", "b200aug_decode_jpeg_gray", "b200aug_jpeg_last_status", "b200aug_jpeg_backend")
 
 
@@ -101,6 +103,8 @@ def _load():
     lib.b200aug_jpeg_last_status.restype = C.c_int
     lib.b200aug_jpeg_backend.restype = C.c_int
     lib.b200aug_hamming_table.restype = C.c_int
+    lib.b200aug_remap_table.restype = C.c_int
+    lib.b200aug_remap_table.argtypes = [C.c_int, C.c_void_p]
     lib.b200aug_head_roi.restype = C.c_int
     lib.b200aug_head_roi.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                      C.c_void_p, C.c_int32, C.c_void_p]

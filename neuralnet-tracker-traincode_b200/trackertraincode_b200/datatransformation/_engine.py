@@ -294,16 +294,40 @@ def hamming_table(device) -> Tuple[torch.Tensor, int]:
     return hit
 
 
-def set_downfilter(args, downfilter: Optional[str], device) -> List[Any]:
-    """Fill B200AugFusedArgs.downfilter (+ the Hamming table); returns what must outlive the launch."""
+UPFILTER_CODES = {None: N.UP_LINEAR, "linear": N.UP_LINEAR, "cubic": N.UP_CUBIC, "lanczos": N.UP_LANCZOS}
+_REMAP_TABLES: Dict[Any, torch.Tensor] = {}
+
+
+def remap_tables(device) -> torch.Tensor:
+    """cv2's fixed-point warpAffine tables for INTER_CUBIC and INTER_LANCZOS4 (B200AugFusedArgs.remap_tabs), cached."""
+    key = (device.type, device.index)
+    hit = _REMAP_TABLES.get(key)
+    if hit is None:
+        host = np.zeros(1024 * 16 + 1024 * 64, np.int16)
+        N.check(N.lib.b200aug_remap_table(N.UP_CUBIC, host.ctypes.data), "b200aug_remap_table")
+        N.check(N.lib.b200aug_remap_table(N.UP_LANCZOS, host[1024 * 16:].ctypes.data), "b200aug_remap_table")
+        hit = _REMAP_TABLES[key] = torch.from_numpy(host).to(device)
+    return hit
+
+
+def set_downfilter(args, downfilter: Optional[str], device, upfilter: Optional[str] = None) -> List[Any]:
+    """Fill B200AugFusedArgs.downfilter / upfilter (+ the Hamming / interpolation tables); returns what must outlive the launch."""
     if downfilter not in DOWNFILTER_CODES:
         raise ValueError(f"downfilter {downfilter!r}: one of 'area', 'gaussian', 'hamming'")
+    if upfilter not in UPFILTER_CODES:
+        raise ValueError(f"upfilter {upfilter!r}: one of 'linear', 'cubic', 'lanczos'")
+    keep: List[Any] = []
     args.downfilter = DOWNFILTER_CODES[downfilter]
     if args.downfilter == N.DOWN_HAMMING:
         taps, mask = hamming_table(device)
         args.hamming_taps, args.hamming_sym_mask = taps.data_ptr(), mask
-        return [taps]
-    return []
+        keep.append(taps)
+    args.upfilter = UPFILTER_CODES[upfilter]
+    if args.upfilter != N.UP_LINEAR:
+        tabs = remap_tables(device)
+        args.remap_tabs = tabs.data_ptr()
+        keep.append(tabs)
+    return keep
 
 
 def _plan_buffer(device, B: int, ow: int, oh: int):
@@ -401,7 +425,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
                   want_view_roi: bool = False, want_status: bool = False, image_key: Optional[str] = None,
                   want_trace: bool = False, use_workspace: bool = True, cluster_size: int = 0,
                   schedule: bool = True, preplan: bool = True, private_scratch: bool = False,
-                  downfilter: Optional[str] = None) -> PreparedCall:
+                  downfilter: Optional[str] = None, upfilter: Optional[str] = None) -> PreparedCall:
     """Marshal one fused call (allocate outputs, upload parameters) without launching it."""
     meta = batch.meta
     batched = meta.prefixshape != ()
@@ -428,7 +452,7 @@ def prepare_fused(batch: Batch, *, flags: int, out_size, geo: Optional[GeoParams
     args.warp_ctas = int(os.environ.get("B200AUG_WARP_CTAS", "0"))  # experiment knob, 0 = library default
     keep: List[Any] = []
     out_data: Dict[str, Any] = {}
-    keep += set_downfilter(args, downfilter, device)
+    keep += set_downfilter(args, downfilter, device, upfilter)
 
     # ---- fields
     image_keys = [k for k in batch.keys() if as_category(meta.categories.get(k)) == FieldCategory.image]

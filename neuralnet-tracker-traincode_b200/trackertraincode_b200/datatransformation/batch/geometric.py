@@ -58,16 +58,16 @@ class NoRoiRandomization:
         return RoiFocusRandomizationParameters(torch.full(B, float(self.extent_factor)), torch.zeros(B), torch.zeros(B + (2,)))
 
 
-def _check_filters(params: RoiFocusRandomizationParameters) -> str:
-    """The down-filter to hand to the kernels ('area' | 'gaussian' | 'hamming', image_geometric_cv2.py:15,47-82).  Of the
-    up-filters only 'linear' exists here (the training sampler's choice, geometric.py:76-77): cubic / lanczos raise."""
+def _check_filters(params: RoiFocusRandomizationParameters):
+    """(downfilter, upfilter) for the kernels: 'area' | 'gaussian' | 'hamming' and 'linear' | 'cubic' | 'lanczos'
+    (image_geometric_cv2.py:15-16, 47-82, 105-119); None = the defaults of :98-99."""
     up = params.upfilter or "linear"
     down = params.downfilter or "area"
-    if up != "linear":
-        raise N.NativeError(f"upfilter {up!r} is not implemented on the B200 path ('linear' is)")
+    if up not in ("linear", "cubic", "lanczos"):
+        raise KeyError(up)  # (the reference's dict lookup, image_geometric_cv2.py:70-75)
     if down not in ("area", "gaussian", "hamming"):
         raise NotImplementedError(f"Filter: {down}")
-    return down
+    return down, up
 
 
 class GeneralFocusRoi:
@@ -96,13 +96,13 @@ class GeneralFocusRoi:
         W, H = sample.meta.image_wh
         B = sample.meta.prefixshape
         params = self.make_randomization_parameters(B)
-        downfilter = _check_filters(params)
+        downfilter, upfilter = _check_filters(params)
         self._maybe_account_for_video(sample.meta, params)
         geo = E.GeoParams(params.scales, params.angles, params.translations, E.host_cos_sin(params.angles))
         res = E.fused_forward(sample, flags=N.F_FOCUS, out_size=self.new_size, geo=geo, roi_variable=self.roi_variable,
                               beyond_border_shift=self._max_beyond_border_shift,
                               insert_backtransform=self.insert_backtransform, rowbuf_capacity=self.rowbuf_capacity,
-                              want_status=True, downfilter=downfilter)
+                              want_status=True, downfilter=downfilter, upfilter=upfilter)
         self.status.watch(res.status, "GeneralFocusRoi")
         # like the reference, the passed sample (and its meta) is updated in place.  An "image_backtransform" that is
         # already there becomes BT @ tr^-1 (affinetrafo.py:137-147) -- unless insert_backtransform starts it afresh as tr^-1

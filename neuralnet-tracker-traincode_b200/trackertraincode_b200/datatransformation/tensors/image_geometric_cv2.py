@@ -27,17 +27,18 @@ def _extract_size_tuple(new_size: Union[int, Tuple[int, int]]):
     return int(new_w), int(new_h)
 
 
-def _check_filters(downfilter, upfilter) -> str:
+def _check_filters(downfilter, upfilter):
     up = "linear" if upfilter is None else upfilter
     down = "area" if downfilter is None else downfilter
-    if up != "linear":
-        raise N.NativeError(f"upfilter {up!r} is not implemented on the B200 path ('linear' is)")
+    if up not in ("linear", "cubic", "lanczos"):
+        raise KeyError(up)
     if down not in ("area", "gaussian", "hamming"):
         raise NotImplementedError(f"Filter: {down}")
-    return down
+    return down, up
 
 
-def _resample(img: torch.Tensor, new_size, view_roi: Optional[torch.Tensor], tr: Optional[torch.Tensor], downfilter: str) -> torch.Tensor:
+def _resample(img: torch.Tensor, new_size, view_roi: Optional[torch.Tensor], tr: Optional[torch.Tensor], filters) -> torch.Tensor:
+    downfilter, upfilter = filters
     if not img.is_cuda:
         raise N.NativeError(f"image lives on {img.device}; the B200 path needs CUDA tensors (there is no CPU fallback)")
     new_w, new_h = _extract_size_tuple(new_size)
@@ -51,7 +52,7 @@ def _resample(img: torch.Tensor, new_size, view_roi: Optional[torch.Tensor], tr:
     args.batch, args.out_w, args.out_h, args.flags = B, new_w, new_h, N.F_FOCUS
     args.roi_field = args.landmark_field = -1
     args.src_uniform, args.src_stride = src.uniform, src.stride
-    keep = [src] + E.set_downfilter(args, downfilter, x.device)
+    keep = [src] + E.set_downfilter(args, downfilter, x.device, upfilter)
     if view_roi is not None:
         v = view_roi.to(x.device, torch.int32).reshape(-1, 4).expand(B, 4).contiguous()
         args.explicit_view_roi = v.data_ptr()

@@ -2,8 +2,8 @@
 B200 mirror API on the GPU: a heat map with three peaks is cropped / rescaled / rotated together with its landmark labels
 and the peaks' centroids must land on the transformed landmarks.  The reference uses a 3-channel float heat map; this path
 is single-channel uint8, so every channel is one call with identical parameters (same arithmetic per channel in cv2).
-The down-filter rows of the reference's table (area / gaussian / hamming) run; the cubic / lanczos up-filters are not on the
-B200 path and must raise."""
+All six rows of the reference's filter table (:175-192) run: linear / cubic / lanczos up, gaussian / hamming / area down
+(SURVEY.md 8 a9)."""
 from functools import partial
 
 import numpy as np
@@ -63,8 +63,8 @@ def with_some_similarity_trafo(B, filter_args):  # :82-88
                                                translations=torch.tensor([-0.1, 0.03]), **filter_args)
 
 
-CONFIGS = [("up", {"upfilter": "linear"}, 0.0), ("down", {"downfilter": "gaussian"}, 0.0), ("down", {"downfilter": "hamming"}, 0.0),
-           ("down", {"downfilter": "area"}, 0.0)]  # the rows of :175-192 on this path
+CONFIGS = [("up", {"upfilter": "linear"}, 0.0), ("up", {"upfilter": "cubic"}, 0.5), ("up", {"upfilter": "lanczos"}, 0.5),
+           ("down", {"downfilter": "gaussian"}, 0.0), ("down", {"downfilter": "hamming"}, 0.0), ("down", {"downfilter": "area"}, 0.0)]  # :175-192
 
 
 @pytest.mark.parametrize("way, filter_args, tol", CONFIGS)
@@ -80,11 +80,9 @@ def test_scalingtrafo_with_randomizer(way, filter_args, tol):  # :206-216
     np.testing.assert_allclose(centroids(image).numpy(), pts[:, :2].numpy(), atol=0.01 + tol + (0.2 if way == "down" else 0.5))
 
 
-@pytest.mark.parametrize("filter_args", [{"upfilter": "cubic"}, {"upfilter": "lanczos"}])
-def test_other_filters_raise(filter_args):
-    from trackertraincode_b200 import _native as N
-
-    with pytest.raises(N.NativeError):
+@pytest.mark.parametrize("filter_args, exc", [({"upfilter": "nearest"}, KeyError), ({"downfilter": "box"}, NotImplementedError)])
+def test_unknown_filters_raise_like_the_reference(filter_args, exc):  # image_geometric_cv2.py:62, 70-75
+    with pytest.raises(exc):
         run_focus("up", partial(no_randomization, filter_args=filter_args))
 
 
