@@ -359,6 +359,7 @@ def run_gpu_arm(args):
     # kernel; events order plan(s) -> main(s) and main(s) -> plan(s + RING) (which rewrites that call's records / labels).
     # Every step's plan AND main phase runs inside the timed region (plan(0) is enqueued after ev0, main(K-1) before ev1).
     pipelined = os.environ.get("B200AUG_BENCH_SERIAL", "") == ""
+    mode = {"two_streams": os.environ.get("B200AUG_BENCH_TWO_STREAMS", "") != ""}
     side = torch.cuda.Stream(dev)
     planned = [torch.cuda.Event() for _ in range(RING)]
     drained = [torch.cuda.Event() for _ in range(RING)]
@@ -368,7 +369,15 @@ def run_gpu_arm(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record(stream)
-        if pipelined:
+        if mode["two_streams"]:
+            # consecutive steps alternate between two streams (each step: plan_kernel, then the big kernel behind a programmatic
+            # dependent launch): steps are independent, so step s + 1 fills the SMs that step s's tail leaves idle
+            side.wait_event(ev0)
+            for s in range(args.steps):
+                calls[s % RING].launch((stream if s % 2 == 0 else side).cuda_stream)  # (RING is even: a call stays on its stream)
+            drained[0].record(side)
+            stream.wait_event(drained[0])
+        elif pipelined:
             side.wait_event(ev0)
             calls[0].launch_plan(side.cuda_stream)
             planned[0].record(side)
@@ -407,6 +416,13 @@ def run_gpu_arm(args):
         wins = tw.cpu().tolist()
     ms = float(np.median(wins))
     value = world * BATCH * args.steps / (ms * 1e-3)
+    # for the record (single GPU): the same K steps with consecutive steps on alternating streams, so that step s + 1 fills the
+    # SMs step s's tail leaves idle -- throughput of overlapped steps, NOT a per-launch time; it does not enter `value`
+    overlapped_ms = None
+    if world == 1 and not args.quick and not mode["two_streams"]:
+        mode["two_streams"] = True
+        overlapped_ms = float(np.median([timed_window() for _ in range(max(3, n_win // 2))]))
+        mode["two_streams"] = False
 
     # ---- end-to-end through the public API from pinned host buffers
     pinned = []
@@ -525,6 +541,9 @@ def run_gpu_arm(args):
                                   "max over ranks per window)",
                         "window_ms": {"min": float(min(wins)), "median": ms, "max": float(max(wins))},
                         "per_rank_ms_per_step": [m / args.steps for m in per_rank],
+                        **({"overlapped_steps": {"ms_per_step": overlapped_ms / args.steps, "samples_per_s": BATCH * args.steps / (overlapped_ms * 1e-3),
+                                                 "note": "consecutive steps on two alternating streams (step s+1 fills the tail of step s); "
+                                                         "throughput only, not the reported value"}} if overlapped_ms else {}),
                         "cpu_affinity_cores": affinity,
                         **({"EXPERIMENT_dropped": os.environ["B200AUG_BENCH_DROP"]} if os.environ.get("B200AUG_BENCH_DROP") else {})},
             "clocks": clocks,

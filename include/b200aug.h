@@ -234,6 +234,10 @@ const char* b200aug_strerror(int code);
 int b200aug_last_cuda_error(void);
 /* dynamic shared memory (bytes) one CTA of the fused kernel uses for this geometry; 0 if it cannot fit */
 size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capacity);
+/* what the driver will co-schedule of the fused kernel for this geometry on the current device: resident CTAs per SM
+ * (registers / shared memory) and the number of clusters of `cluster_size` (0 = default) CTAs active at once
+ * (cudaOccupancyMaxActiveClusters) */
+int b200aug_fused_occupancy(int out_w, int out_h, int rowbuf_capacity, int cluster_size, int* ctas_per_sm, int* active_clusters);
 /* bytes of scratch per sample that hold the rotated canvas of a crop box of up to max_side x max_side source pixels */
 int64_t b200aug_workspace_stride(int max_side);
 /* bytes of one record of B200AugFusedArgs::plans for this output size, and of the whole buffer for `batch` samples */

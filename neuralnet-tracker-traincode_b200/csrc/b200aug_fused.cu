@@ -2932,6 +2932,31 @@ extern "C" size_t b200aug_fused_smem_bytes(int out_w, int out_h, int rowbuf_capa
   return t <= 227 * 1024 ? t : 0;
 }
 
+extern "C" int b200aug_fused_occupancy(int out_w, int out_h, int rowbuf_capacity, int cluster_size, int* ctas_per_sm, int* active_clusters) {
+  if (out_w <= 0 || out_h <= 0 || !ctas_per_sm || !active_clusters) return B200AUG_E_INVALID_ARG;
+  int cap = rowbuf_capacity > 0 ? rowbuf_capacity : DEFAULT_ROWBUF;
+  cap = (cap + 15) & ~15;
+  const size_t smem = smem_layout(out_w, out_h, cap).total;
+  if (smem > 227 * 1024) return B200AUG_E_SMEM;
+  const int cl = cluster_size > 0 ? cluster_size : DEFAULT_CLUSTER;
+  cudaError_t e = cudaFuncSetAttribute(fused_augment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fused_augment_kernel<false>, NTHREADS, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 * 8 * cl);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(active_clusters, fused_augment_kernel<false>, &cfg);
+  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return B200AUG_E_CUDA; }
+  return B200AUG_OK;
+}
+
 extern "C" int64_t b200aug_plan_stride(int out_w, int out_h) {
   if (out_w <= 0 || out_h <= 0) return 0;
   return (int64_t)(plan_bytes() + plan_tab_bytes(out_w, out_h));

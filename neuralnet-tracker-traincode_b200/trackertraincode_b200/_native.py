@@ -54,7 +54,7 @@ class FusedArgs(C.Structure):
                 ("photo", PhotoParams)]
 
 
-EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes",
+EXPORTS = ("b200aug_abi_version", "b200aug_strerror", "b200aug_last_cuda_error", "b200aug_fused_smem_bytes", "b200aug_fused_occupancy",
            "b200aug_workspace_stride", "b200aug_plan_stride", "b200aug_plan_buffer_bytes", "b200aug_hamming_table", "b200aug_remap_table", "b200aug_upload_row_bands", "b200aug_upload_boxes", "b200aug_fused_forward", "b200aug_apply_affine2d", "b200aug_photometric_f32", "b200aug_corrected_rotation",
            "b200aug_quat_matrix", "b200aug_head_roi", "b200aug_jpeg_info", "b200aug_decode_jpeg_gray", "b200aug_jpeg_last_status", "b200aug_jpeg_backend")
 
@@ -103,6 +103,8 @@ def _load():
     lib.b200aug_jpeg_last_status.restype = C.c_int
     lib.b200aug_jpeg_backend.restype = C.c_int
     lib.b200aug_hamming_table.restype = C.c_int
+    lib.b200aug_fused_occupancy.restype = C.c_int
+    lib.b200aug_fused_occupancy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.b200aug_remap_table.restype = C.c_int
     lib.b200aug_remap_table.argtypes = [C.c_int, C.c_void_p]
     lib.b200aug_head_roi.restype = C.c_int

@@ -29,9 +29,15 @@ call = E.prepare_fused(b, flags=flags, out_size=bench.OUT, geo=geo, do_flip=torc
                        rot_dir=torch.from_numpy(gp.rot_dir), photo=photo, want_status=True, want_trace=True, want_view_roi=True,
                        cluster_size=int(os.environ.get("B200AUG_CLUSTER", "0")))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+SPLIT = os.environ.get("B200AUG_TRACE_SPLIT")  # plan phase, device idle, then the main phase alone (no overlap with plan_kernel)
 for _ in range(5):
     flush.zero_()
-    call.launch()
+    if SPLIT:
+        call.launch_plan()
+        torch.cuda.synchronize()
+        call.launch_main()
+    else:
+        call.launch()
 torch.cuda.synchronize()
 t = call.result.trace.cpu().numpy().astype(np.int64)
 CL = int(os.environ.get("B200AUG_CLUSTER", "0")) or 2
