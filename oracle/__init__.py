@@ -14,7 +14,13 @@ Parity pinning:
     container (`tests/golden/make_golden.py` -> `tests/golden/*.npz`) and against the reference's own
     known-answer vectors (`test/test_affine_img_trafo.py:49-69`);
   * OpenCV arithmetic (`oracle/cv2_model.py`): pinned bit-exact against the live cv2 binary (same wheel on
-    the GPU box) in `tests/test_oracle_cv2_model.py`;
-  * photometric half (kornia): **parity unpinned** -- kornia is not installed anywhere we can run and the
-    reference has no test for it; `oracle/photometric.py` freezes the written specification of SURVEY.md 8(c).
+    the GPU box) in `tests/test_oracle_cv2_model.py`; the anti-alias down-filters and the cubic / Lanczos
+    up-filters in `tests/test_oracle_prefilter.py` / `tests/test_oracle_upfilters.py` (against cv2 and against
+    reference outputs, `tests/golden/prefilter.npz`, `upfilter.npz`);
+  * head-model roi (`oracle/headmodel.py`): reference outputs with its real face model (`tests/golden/headroi.npz`);
+  * evaluation-side back-transform chain, rotation labels: `tests/golden/backtransform.npz`, `perspective.npz`;
+  * photometric half (kornia): **parity unpinned against kornia itself** -- kornia is not installed anywhere we
+    can run and the reference has no test for it; `oracle/photometric.py` freezes the written specification of
+    SURVEY.md 8(c) and is pinned against the torch primitives kornia calls (`oracle/photometric_torch.py`,
+    `tests/test_oracle_photometric_torch.py`, `tests/test_gpu_photometric_torch.py`).
 """
