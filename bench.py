@@ -368,6 +368,7 @@ def run_gpu_arm(args):
     pipelined = os.environ.get("B200AUG_BENCH_SERIAL", "") == ""
     mode = {"two_streams": os.environ.get("B200AUG_BENCH_TWO_STREAMS", "") != ""}
     side = torch.cuda.Stream(dev)
+    peer = torch.cuda.Stream(dev, priority=-1) if prio else side  # second stream of the overlapped-steps measurement (same priority)
     planned = [torch.cuda.Event() for _ in range(RING)]
     drained = [torch.cuda.Event() for _ in range(RING)]
 
@@ -379,10 +380,10 @@ def run_gpu_arm(args):
         if mode["two_streams"]:
             # consecutive steps alternate between two streams (each step: plan_kernel, then the big kernel behind a programmatic
             # dependent launch): steps are independent, so step s + 1 fills the SMs that step s's tail leaves idle
-            side.wait_event(ev0)
+            peer.wait_event(ev0)
             for s in range(args.steps):
-                calls[s % RING].launch((stream if s % 2 == 0 else side).cuda_stream)  # (RING is even: a call stays on its stream)
-            drained[0].record(side)
+                calls[s % RING].launch((stream if s % 2 == 0 else peer).cuda_stream)  # (RING is even: a call stays on its stream)
+            drained[0].record(peer)
             stream.wait_event(drained[0])
         elif pipelined:
             side.wait_event(ev0)
