@@ -61,14 +61,15 @@ def no_randomization(B: int, extent_factor: float) -> GeoParams:
 
 
 def augment_sample(sample: Sample, scale, angle, translation, do_flip, rot_dir, new_size=129, roi_mode="original",
-                   use_model=False, half_pixel=True, normalize=True, downfilter="area"):
+                   use_model=False, half_pixel=True, normalize=True, downfilter="area", upfilter="linear"):
     """The per-sample half for one sample; returns (Sample, intermediates)."""
     s = nrm.offset_points_by_half_pixel(sample) if half_pixel else sample
     if roi_mode == "landmarks":
         s = geo.put_roi_from_landmarks(s)
     elif roi_mode != "original":
         raise NotImplementedError("extent_to_forehead needs the BFM face model; out of the hot-path scope")
-    s, inter = geo.focus_roi(s, RoiFocusParams(scale, angle, tuple(translation)), new_size, use_model=use_model, downfilter=downfilter)
+    s, inter = geo.focus_roi(s, RoiFocusParams(scale, angle, tuple(translation)), new_size, use_model=use_model, downfilter=downfilter,
+                              upfilter=upfilter)
     if roi_mode == "landmarks":
         s = geo.put_roi_from_landmarks(s)
     s = geo.horizontal_flip_and_rot_90(s, bool(do_flip), int(rot_dir))
@@ -83,12 +84,12 @@ def collate(samples: Sequence[Sample]) -> Dict[str, np.ndarray]:
 
 
 def augment_batch(samples: Sequence[Sample], gp: GeoParams, pp: Optional[pho.PhotoParams], new_size=129,
-                  roi_mode="original", use_model=False, whiten=True, downfilter="area"):
+                  roi_mode="original", use_model=False, whiten=True, downfilter="area", upfilter="linear"):
     """Full chain on a list of source samples.  Returns (dict of stacked outputs, dict of stacked intermediates)."""
     outs, inters = [], []
     for i, s in enumerate(samples):
         o, it = augment_sample(s, gp.scales[i], gp.angles[i], gp.translations[i], gp.do_flip[i], gp.rot_dir[i],
-                               new_size, roi_mode, use_model, downfilter=downfilter)
+                               new_size, roi_mode, use_model, downfilter=downfilter, upfilter=upfilter)
         outs.append(o)
         inters.append(it)
     batch = collate(outs)

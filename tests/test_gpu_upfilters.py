@@ -104,3 +104,49 @@ def test_random_upscaling_against_the_models():
             out = dtt.affine_transform_image_cv2(img, tr, (ow, oh), downfilter=down, upfilter=kind)
             model = geo.affine_transform_image(frame, tr.tensor().numpy(), (ow, oh), use_model=True, downfilter=down, upfilter=kind)
         assert np.array_equal(out.cpu().numpy()[0], model), (t, kind, down)
+
+
+def test_full_chain_with_filters_on_a_mixed_batch():
+    """One fused call -- half-pixel, focus with downfilter='gaussian' / 'hamming' and upfilter='lanczos', flip / rot90, normalise,
+    photometric chain, whiten -- on a batch that mixes shrinking, growing, rotated and border-crossing crops, against the
+    oracle's full chain sample by sample."""
+    import bench
+    from oracle import photometric as opho, pipeline as opipe
+    from oracle.geometric import Sample
+    from trackertraincode_b200 import _native as N
+    from trackertraincode_b200.datasets.batch import Batch, FieldCategory, Metadata
+    from trackertraincode_b200.datatransformation import _engine as E
+
+    B, S = 48, 129
+    host = bench.make_host_batch(21, B)
+    rng = np.random.default_rng(4)
+    small = np.arange(B) % 3 == 0  # tiny faces: the crop grows (up-filter); rotated ones take the up-scaling warp
+    c = 0.5 * (host["roi"][:, :2] + host["roi"][:, 2:])
+    host["roi"][small] = np.concatenate([c[small] - rng.uniform(25, 45, (int(small.sum()), 2)), c[small] + rng.uniform(25, 45, (int(small.sum()), 2))], 1).astype(np.float32)
+    host["roi"][1::7, [0, 2]] -= 150.0  # boxes over the left frame border
+    gp, pp = bench.draw_params(77, B, 9000)
+    cats = {k: FieldCategory(v) for k, v in bench.CATS.items()}
+    dev = {k: torch.from_numpy(v).cuda() for k, v in host.items()}
+    flags = N.F_HALF_PIXEL | N.F_FOCUS | N.F_FLIPROT | N.F_NORMALIZE | N.F_PHOTOMETRIC | N.F_WHITEN
+    an = torch.from_numpy(gp.angles)
+    photo = E.PhotoParams(pp.order, torch.from_numpy(pp.apply), torch.from_numpy(pp.bits), torch.from_numpy(pp.gamma), torch.from_numpy(pp.contrast),
+                          torch.from_numpy(pp.brightness), torch.from_numpy(pp.noise_apply), pp.noise_std, pp.seed, pp.sample_offset, pp.clip)
+    for down in ("gaussian", "hamming"):
+        b = Batch(Metadata((bench.SRC, bench.SRC), B, "t", None, dict(cats)), dict(dev))
+        geo = E.GeoParams(torch.from_numpy(gp.scales), an, torch.from_numpy(gp.translations), E.host_cos_sin(an))
+        r = E.fused_forward(b, flags=flags, out_size=S, geo=geo, do_flip=torch.from_numpy(gp.do_flip.astype(np.uint8)),
+                            rot_dir=torch.from_numpy(gp.rot_dir), photo=photo, want_status=True, downfilter=down, upfilter="lanczos")
+        assert not r.status.cpu().numpy().any()
+        img = r.batch["image"].cpu().numpy()
+        pts = r.batch["pt3d_68"].cpu().numpy()
+        grew = 0
+        for i in range(B):
+            s1 = [Sample((bench.SRC, bench.SRC), {k: (host[k][i][..., None] if k == "image" else host[k][i]) for k in bench.CATS}, bench.CATS)]
+            g1 = opipe.GeoParams(*(x[i:i + 1] for x in (gp.scales, gp.angles, gp.translations, gp.do_flip, gp.rot_dir)))
+            want, inter = opipe.augment_batch(s1, g1, pp.slice(i, i + 1), S, use_model=True, downfilter=down, upfilter="lanczos")
+            v = inter["view_roi"][0]
+            grew += int(v[2] - v[0] < S)
+            err = np.abs(img[i] - want["image"][0]).max()
+            assert err <= 1e-5, (down, i, err)  # (kernel == oracle models, incl. the float32 hamming path)
+            np.testing.assert_allclose(pts[i], want["pt3d_68"][0], rtol=1e-4, atol=2e-5)
+        assert grew >= 8  # the up-filter really ran
