@@ -2212,18 +2212,46 @@ __global__ void __launch_bounds__(NTHREADS, 3) fused_augment_kernel(const __grid
         const bool yhf = ynf & (1 << 30), yhl = ynf & (1u << 31);
         const float yaf = T.a[ow + dy], yam = T.b[ow + dy], yal = T.c[ow + dy];
         float acc = 0.f;
-        for (int k = 0; k < yn; ++k) {
+        // The first TAIL_ROWS canvas rows of the pixel: every tap is loaded unconditionally from a clamped (always valid)
+        // address and masked afterwards, so the TAIL_ROWS x KMAX loads are independent and in flight together (a guarded
+        // load per tap compiles to a branch per tap, i.e. one L2 round trip after the other: 5 us of the step).
+        constexpr int TAIL_ROWS = 4;
+        uint32_t px[TAIL_ROWS][KMAX];
+#pragma unroll
+        for (int k = 0; k < TAIL_ROWS; ++k) {
+          const int sy = y0 + ys + k;
+          const bool row_in = k < yn && (unsigned)sy < (unsigned)sh;
+          const uint8_t* row = src + (ptrdiff_t)min(max(sy, 0), sh - 1) * pitch;
+#pragma unroll
+          for (int t = 0; t < KMAX; ++t) {
+            const int sx = x0 + xs + t;
+            const uint32_t v = row[min(max(sx, 0), sw - 1)];  // (coherent load: the source may be the scratch canvas)
+            px[k][t] = (row_in && t < xn && (unsigned)sx < (unsigned)sw) ? v : 0u;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < TAIL_ROWS; ++k) {
+          if (k < yn) {
+            float h = 0.f;
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t)
+              if (t < xn) h = __fadd_rn(h, __fmul_rn((float)px[k][t], area_alpha(t, xn, xhf, xhl, xaf, xam, xal)));
+            const float beta = area_alpha(k, yn, yhf, yhl, yaf, yam, yal);
+            acc = (k == 0) ? __fmul_rn(beta, h) : __fadd_rn(acc, __fmul_rn(beta, h));
+          }
+        }
+        for (int k = TAIL_ROWS; k < yn; ++k) {  // (scale factors above 3: the remaining rows one tap after the other)
           const int sy = y0 + ys + k;
           const bool row_in = (unsigned)sy < (unsigned)sh;
           const uint8_t* row = src + (ptrdiff_t)sy * pitch + (x0 + xs);
           float h = 0.f;
           for (int t = 0; t < xn; ++t) {
             const bool in = row_in && (unsigned)(x0 + xs + t) < (unsigned)sw;
-            const float px = in ? (float)row[t] : 0.f;  // (coherent load: the source may be the scratch canvas)
-            h = __fadd_rn(h, __fmul_rn(px, area_alpha(t, xn, xhf, xhl, xaf, xam, xal)));
+            const float px1 = in ? (float)row[t] : 0.f;
+            h = __fadd_rn(h, __fmul_rn(px1, area_alpha(t, xn, xhf, xhl, xaf, xam, xal)));
           }
           const float beta = area_alpha(k, yn, yhf, yhl, yaf, yam, yal);
-          acc = (k == 0) ? __fmul_rn(beta, h) : __fadd_rn(acc, __fmul_rn(beta, h));
+          acc = __fadd_rn(acc, __fmul_rn(beta, h));
         }
         const uint8_t q = sat_u8_rint(acc);
         if (direct) gimg[tm.o + dy * tm.sa + dx * tm.sb] = lut[q];
