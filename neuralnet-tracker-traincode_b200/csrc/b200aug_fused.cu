@@ -1127,8 +1127,12 @@ __device__ __noinline__ void area_band(const TileMap tm, int cap, int ow, int oh
       if (fetch) {
         const uintptr_t g16 = (g & ~uintptr_t(15)) + lane16;
         const uint32_t d16 = dst_lane + (uint32_t)soff;
-        if (my_vecs > 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d16), "l"(g16) : "memory");
-        if (my_vecs > 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d16 + 512u), "l"(g16 + 512u) : "memory");
+        // (predicated copies: an `if` around the asm compiles to a divergent branch + reconvergence per copy and row)
+        asm volatile(
+            "{\n.reg .pred p0, p1;\nsetp.gt.s32 p0, %2, 0;\nsetp.gt.s32 p1, %2, 1;\n"
+            "@p0 cp.async.cg.shared.global [%0], [%1], 16;\n@p1 cp.async.cg.shared.global [%0+512], [%1+512], 16;\n}" ::"r"(d16),
+            "l"(g16), "r"(my_vecs)
+            : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
